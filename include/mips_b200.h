@@ -1,0 +1,154 @@
+/*
+ * mips_b200.h — C ABI of the B200-native exact MIPS index (libmips_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of florianbaud/retrieval-augmented-mds:
+ * the flat exact index behind `Mips.search` (reference sotasum/mips.py:382-400), i.e. what
+ * the reference reaches through HF-datasets' FaissIndex -> faiss.IndexFlat{IP,L2}
+ * (call sites sotasum/mips.py:333-340 add, :383-386 search; retriever_lightning.py:317-321,
+ * :400-404; pretrain.py:475-479, :519-523), plus the build-side row statistics of
+ * `Mips.build_index` (mips.py:290-345) and the doc-score arithmetic of
+ * retriever_generator.py:158-193.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a raw host or device address.
+ *   - return 0 on success, negative MIPS_E_* on error; message via mips_last_error()
+ *     (thread local). Nothing throws across the ABI.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). All device
+ *     work is enqueued on it; calls do not synchronise unless documented ("sync").
+ *   - ids are int64 like faiss; missing results are id -1 with score -inf (IP) / +inf (L2).
+ *   - one index per process/GPU; add and search on one index must not overlap.
+ */
+#ifndef MIPS_B200_H_
+#define MIPS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mips_index_s* mips_handle;
+
+/* faiss.METRIC_INNER_PRODUCT / faiss.METRIC_L2 (reference mips.py:306,316,369,371). */
+#define MIPS_METRIC_IP 0
+#define MIPS_METRIC_L2 1
+
+/* Storage / arithmetic type of the bank shard in HBM. */
+#define MIPS_DTYPE_F32 0   /* fp32 rows, exact fp32 FMA search (SIMT)              */
+#define MIPS_DTYPE_BF16 1  /* bf16 rows, tcgen05 tensor-core search, fp32 accumulate */
+
+/* Search kernel selection (testing / bisection; AUTO is what the product uses). */
+#define MIPS_ALGO_AUTO 0
+#define MIPS_ALGO_SIMT 1   /* fp32 FMA tiled kernel, any dtype                     */
+#define MIPS_ALGO_TC 2     /* tcgen05/TMEM/TMA kernel, bf16 bank, d_pad <= 768     */
+
+/* Output transform applied by the merge kernel to the ranking key. */
+#define MIPS_OUT_IP 0      /* D = <q,x>                    descending (IndexFlatIP)          */
+#define MIPS_OUT_L2 1      /* D = |q|^2+|x|^2-2<q,x>       ascending  (IndexFlatL2)          */
+#define MIPS_OUT_AUGL2 2   /* D = |q|^2+phi-2<q,x>         ascending  (IndexFlatL2 on the
+                              augment_xb/augment_xq vectors of mips.py:55-70, no extra column) */
+
+#define MIPS_E_INVALID -1  /* bad argument / shape / dtype    */
+#define MIPS_E_CUDA -2     /* CUDA runtime or driver error    */
+#define MIPS_E_NOMEM -3    /* allocation failed               */
+#define MIPS_E_UNSUPPORTED -4
+
+#define MIPS_MAX_K 64      /* per-pass top-k capacity of the search kernels */
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* Replaces faiss.index_factory(d, "Flat", metric) / IndexFlatIP(d) / IndexFlatL2(d)
+ * (reference mips.py:333-340 via datasets.add_faiss_index; mips.py:665,670).
+ * capacity_rows > 0 pre-sizes the HBM shard (no regrowth while ntotal <= capacity). */
+int mips_create(mips_handle* out, int d, int metric, int dtype, int device, int64_t capacity_rows);
+int mips_destroy(mips_handle h);
+/* faiss Index.reset(): drop all rows, keep the allocation. */
+int mips_reset(mips_handle h);
+int64_t mips_ntotal(mips_handle h);
+int mips_dim(mips_handle h);
+int mips_metric(mips_handle h);
+int mips_dtype(mips_handle h);
+
+/* ---- build side (K0) -------------------------------------------------------------------- */
+
+/* Replaces faiss Index.add(x) as driven by datasets' add_vectors in 1000-row batches
+ * (reference mips.py:333-340) fused with the per-row passes of Mips.build_index:
+ * _map_norm (mips.py:347-349), _map_normalize (:358-361, when normalize != 0) and the
+ * row |x|^2 needed by get_phi/augment_xb (:55-65). x: fp32 [n, d] row-major, host
+ * (x_on_device = 0; staged through pinned memory, sync) or device (x_on_device = 1, async). */
+int mips_add(mips_handle h, const float* x, int64_t n, int x_on_device, int normalize, void* stream);
+
+/* max_i |x_i|^2 over the rows as given to mips_add (before normalisation) = get_phi(xb)
+ * (mips.py:55-56) and max_norm^2 (mips.py:298-304). Sync on `stream`. */
+int mips_max_norm2(mips_handle h, float* out, void* stream);
+/* phi used by MIPS_OUT_AUGL2; set after the cross-rank MAX. */
+int mips_set_phi(mips_handle h, float phi);
+float mips_get_phi(mips_handle h);
+
+/* faiss.normalize_L2(x) (reference mips.py:521-525): in-place row normalisation of fp32 [n, d]
+ * (host: staged to the device and back, sync; device: async). Rows with zero norm untouched. */
+int mips_normalize_l2(float* x, int64_t n, int d, int x_on_device, int device, void* stream);
+
+/* Copy rows [row0, row0+n) back as fp32 [n, d] (host or device). Used by save()/np_search. */
+int mips_reconstruct(mips_handle h, int64_t row0, int64_t n, float* out, int out_on_device, void* stream);
+
+/* ---- search side (K1 + K2) -------------------------------------------------------------- */
+
+/* Local (one shard) exact top-k. Replaces faiss Index.search(xq, k) for this shard
+ * (reference mips.py:383-386) with the ignore filter of mips.py:388-398 fused in
+ * ("exclude id == ignore_ids[j] for query j", ids are GLOBAL = id_offset + local row).
+ *   q            device fp32 [nq, d]
+ *   q_normalize  != 0: L2-normalise each query first (_prepare_query, mips.py:368-370)
+ *   ignore_ids   device int64 [nq] or NULL
+ *   out_key      device fp32 [nq, k]  ranking key, descending: <q,x> (IP) or <q,x>-|x|^2/2 (L2)
+ *   out_ids      device int64 [nq, k] global ids, -1 padded
+ *   out_xnorm2   device fp32 [nq, k] or NULL: |x|^2 of each hit (for cosine / L2 output)
+ *   out_qnorm2   device fp32 [nq] or NULL: |q|^2 (after optional normalisation)
+ * 1 <= k <= MIPS_MAX_K. Async on `stream`. */
+int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normalize,
+                      const int64_t* ignore_ids, int64_t id_offset, int algo,
+                      float* out_key, int64_t* out_ids, float* out_xnorm2, float* out_qnorm2,
+                      void* stream);
+
+/* k-way merge of n_parts candidate lists per query (after the cross-GPU all-gather, or of a
+ * single list) + output transform + the doc-score arithmetic of retriever_generator.py:158-193.
+ *   cand_key/cand_ids/cand_xnorm2  device [n_parts, nq, k_in]   (cand_xnorm2 may be NULL if
+ *                                  neither L2 output nor cosine is requested)
+ *   q_norm2      device [nq] or NULL (required for L2/AUGL2/cosine)
+ *   D, I         device [nq, k_out] final scores (per out_mode) and ids
+ *   cosine       device [nq, k_out] or NULL:  <q,x>/(|q||x|)   (retriever_generator.py:159-172)
+ *   doc_prob     device [nq, k_out] or NULL:  softmax_j(beta*cosine_j + beta_bias)
+ *                (the per-document factor of decoder_own.py:110-114,134)
+ *   memory_bias  device [nq, k_out*mem_len] or NULL: cosine broadcast over each doc's tokens
+ *                (retriever_generator.py:188-192)
+ * Async on `stream`. */
+int mips_merge(const float* cand_key, const int64_t* cand_ids, const float* cand_xnorm2,
+               int n_parts, int nq, int k_in, int k_out, int metric, int out_mode, float phi,
+               const float* q_norm2, const int64_t* ignore_ids,
+               float* D, int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias,
+               float* memory_bias, int mem_len, void* stream);
+
+/* End-to-end host call: what `Mips.search` does today with numpy in / numpy out
+ * (reference mips.py:382-400). H2D of queries, K1, K2, D2H of (D, I); sync.
+ * xq host fp32 [nq, d]; ignore_ids host int64 [nq] or NULL; D host fp32 [nq,k]; I host int64 [nq,k]. */
+int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normalize,
+                     const int64_t* ignore_ids, int out_mode, float* D, int64_t* I, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+const char* mips_last_error(void);
+/* Number of kernels this library has launched so far in this process (bench gpu_launches). */
+int64_t mips_launch_count(void);
+/* Name of the search kernel the last mips_search_local call used ("tc" / "simt"). */
+const char* mips_last_algo(mips_handle h);
+/* K1 timing: with profiling on, every search records a CUDA-event pair around its K1 launch on
+ * the caller's stream (no sync). mips_k1_ms_total() synchronises on those events and returns the
+ * SUM of the K1 durations (ms) recorded since mips_set_profiling(h, 1) (at most 256 launches are
+ * kept); mips_prof_count() says how many launches that sum covers. */
+int mips_set_profiling(mips_handle h, int on);
+float mips_k1_ms_total(mips_handle h);
+int mips_prof_count(mips_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIPS_B200_H_ */

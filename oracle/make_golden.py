@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN CODE on seeded inputs.
+
+`import sotasum.mips` is impossible in this image (top-level `import faiss`, `adapters`,
+`pytorch_lightning`), so the functions and statements on the hot path are extracted from the
+reference sources by AST / source segment and executed unmodified:
+
+  sotasum/mips.py            inner_product, get_phi, augment_xb, augment_xq, _layer_norm,
+                             the body of Mips.search (with a stub index whose .search is the
+                             reference's inner_product), Mips._prepare_query (with
+                             faiss.normalize_L2 replaced by its documented contract)
+  sotasum/pretrain.py        retriever_metrics
+  sotasum/retriever_generator.py   the doc-score statements :158-172 and :188-192
+
+Run here (needs /root/reference):   python oracle/make_golden.py
+The .npz files are small and committed; the GPU box never reads /root/reference.
+"""
+from __future__ import annotations
+
+import ast
+import sys
+import textwrap
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = Path("/root/reference/sotasum")
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _extract(path: Path, names: set[str], method_of: str | None = None) -> dict:
+    src = path.read_text()
+    tree = ast.parse(src)
+    ns = {"np": np, "torch": torch}
+    found = {}
+    nodes = tree.body
+    if method_of:
+        cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == method_of)
+        nodes = cls.body
+    for n in nodes:
+        if isinstance(n, ast.FunctionDef) and n.name in names:
+            code = textwrap.dedent(ast.get_source_segment(src, n))
+            # drop decorators (rank_zero_only etc.) — they are not part of the arithmetic
+            code = code[code.index("def "):]
+            exec(compile(code, f"{path}:{n.lineno}", "exec"), ns)
+            found[n.name] = ns[n.name]
+    missing = names - set(found)
+    assert not missing, f"not found in {path}: {missing}"
+    return found
+
+
+def _statements(path: Path, first: int, last: int) -> str:
+    """Source of whole statements whose line span lies inside [first, last] of a function body."""
+    src = path.read_text()
+    tree = ast.parse(src)
+    out = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.stmt) and not isinstance(node, (ast.FunctionDef, ast.ClassDef, ast.If)):
+            if node.lineno >= first and node.end_lineno <= last and isinstance(
+                    node, (ast.Assign, ast.AugAssign, ast.AnnAssign, ast.With, ast.Expr)):
+                out.append((node.lineno, node.end_lineno, textwrap.dedent(ast.get_source_segment(src, node))))
+    # keep outermost statements only
+    out.sort()
+    keep, last_end = [], -1
+    for a, b, s in out:
+        if a > last_end:
+            keep.append(s)
+            last_end = b
+    return "\n".join(keep)
+
+
+def main() -> None:
+    OUT.mkdir(parents=True, exist_ok=True)
+    mips_py = REF / "mips.py"
+    fns = _extract(mips_py, {"inner_product", "get_phi", "augment_xb", "augment_xq", "_layer_norm"})
+    inner_product, get_phi = fns["inner_product"], fns["get_phi"]
+    augment_xb, augment_xq = fns["augment_xb"], fns["augment_xq"]
+    meth = _extract(mips_py, {"search", "_prepare_query", "l2_normalization"}, method_of="Mips")
+    metrics = _extract(REF / "pretrain.py", {"retriever_metrics"})["retriever_metrics"]
+
+    rng = np.random.default_rng(20231018)
+
+    # ---- G1: inner_product, both normalize settings (mips.py:552-560)
+    xb = rng.standard_normal((2048, 96), dtype=np.float32) * rng.uniform(0.5, 2.0, (2048, 1)).astype(np.float32)
+    xq = rng.standard_normal((24, 96), dtype=np.float32)
+    np.savez_compressed(OUT / "inputs.npz", xb=xb, xq=xq)  # shared by the fixtures below
+    g = {}
+    for norm in (False, True):
+        for k in (1, 8, 10):
+            s, i = inner_product(xq, xb, k, normalize=norm)
+            g[f"scores_n{int(norm)}_k{k}"] = s.astype(np.float32)
+            g[f"ids_n{int(norm)}_k{k}"] = i.astype(np.int64)
+    np.savez_compressed(OUT / "inner_product.npz", **g)
+
+    # ---- G2: L2 augmentation helpers + the IP == L2-on-augmented identity (mips.py:55-70, 655-685)
+    def _aug_case(bank, queries):
+        phi = get_phi(bank)
+        bank_aug = augment_xb(bank)
+        q_aug = augment_xq(queries)
+        # exact L2 on the augmented vectors (what IndexFlatL2(d+1) computes), float64 then ranked
+        d2 = ((q_aug[:, None, :].astype(np.float64) - bank_aug[None, :, :].astype(np.float64)) ** 2).sum(-1)
+        ids_l2 = np.argsort(d2, axis=1, kind="stable")[:, :10]
+        s_ip, ids_ip = inner_product(queries, bank, 10, normalize=False)
+        return dict(phi=np.float32(phi), extracol=bank_aug[:, -1].astype(np.float32), xq_aug=q_aug.astype(np.float32),
+                    ids_l2=ids_l2.astype(np.int64), d2=np.take_along_axis(d2, ids_l2, 1),
+                    ids_ip=ids_ip.astype(np.int64), scores_ip=s_ip.astype(np.float32))
+
+    case_a = _aug_case(xb, xq[:8])                       # rows with very different norms
+    lay = fns["_layer_norm"](torch.tensor(xb[:256])).numpy()   # the setting of test_faiss_index
+    case_b = _aug_case(lay, lay[:2])
+    np.savez_compressed(OUT / "augment.npz", layer_norm_rows=lay, **case_a,
+                        **{f"ln_{k}": v for k, v in case_b.items()})
+
+    # ---- G3: Mips.search with and without ignore_indexes (mips.py:382-400), the reference's own
+    # method body run against a stub index backed by the reference's inner_product.
+    class _FaissIndex:
+        def search(self, queries, k):
+            return inner_product(queries, xb, k, normalize=False)
+
+    class _Holder:
+        faiss_index = _FaissIndex()
+
+    class _Emb:
+        def get_index(self, name):
+            return _Holder()
+
+    stub = types.SimpleNamespace(embeddings=_Emb(), index_name="mips_embeddings")
+    ign = [int(v) for v in rng.integers(0, xb.shape[0], xq.shape[0])]
+    # make half of the ignore ids actual top hits so the filter does something
+    top1 = inner_product(xq, xb, 1, normalize=False)[1][:, 0]
+    for j in range(0, len(ign), 2):
+        ign[j] = int(top1[j])
+    s0, i0 = meth["search"](stub, xq, None, 10)
+    s1, i1 = meth["search"](stub, xq, ign, 10)
+    np.savez_compressed(OUT / "mips_search.npz", ignore=np.asarray(ign, dtype=np.int64),
+                        scores_plain=np.asarray(s0, dtype=np.float32), ids_plain=np.asarray(i0, dtype=np.int64),
+                        scores_ignore=np.asarray(s1, dtype=np.float32), ids_ignore=np.asarray(i1, dtype=np.int64))
+
+    # ---- G4: _prepare_query (mips.py:368-375); faiss.normalize_L2 is third party: its documented
+    # contract (x *= 1/sqrt(|x|^2), zero rows untouched) is supplied as the stand-in.
+    def _normalize_L2(x):
+        n2 = (x * x).sum(1)
+        nz = n2 > 0
+        x[nz] *= (1.0 / np.sqrt(n2[nz]))[:, None]
+
+    faiss_stub = types.SimpleNamespace(METRIC_INNER_PRODUCT=0, METRIC_L2=1, normalize_L2=_normalize_L2)
+    meth["_prepare_query"].__globals__["faiss"] = faiss_stub
+    meth["_prepare_query"].__globals__["augment_xq"] = augment_xq
+    pq = {}
+    xq_z = xq.copy()
+    xq_z[3] = 0.0
+    for metric, norm in ((0, True), (0, False), (1, True)):
+        me = types.SimpleNamespace(normalize=norm, metric_type=metric)
+        me.l2_normalization = types.MethodType(meth["l2_normalization"], me)
+        pq[f"m{metric}_n{int(norm)}"] = meth["_prepare_query"](me, xq_z.copy())
+    np.savez_compressed(OUT / "prepare_query.npz", xq=xq_z, **pq)
+
+    # ---- G5: retriever_metrics (pretrain.py:69-85)
+    pred = (rng.uniform(size=(32, 10)) < 0.25).astype(np.float32)
+    counts = np.maximum(pred.sum(-1), 1) + rng.integers(0, 3, 32).astype(np.float32)
+    m = metrics(torch.tensor(pred), torch.tensor(counts))
+    np.savez_compressed(OUT / "retriever_metrics.npz", pred=pred, counts=counts,
+                        recall=np.float32(m["recall"]), reciprocal_rank=np.float32(m["reciprocal_rank"]),
+                        average_precision=np.float32(m["average_precision"]))
+
+    # ---- G6: doc-score statements of SotasumEncoder.forward (retriever_generator.py:158-172,188-192)
+    rg = REF / "retriever_generator.py"
+    code = _statements(rg, 158, 172) + "\n" + _statements(rg, 180, 192)
+    B, K, L, d = 6, 5, 7, 96
+    query = torch.tensor(rng.standard_normal((B, 1, d), dtype=np.float32))
+    hid = torch.tensor(rng.standard_normal((B, K, L, d), dtype=np.float32))
+    mem = torch.tensor(rng.standard_normal((B * K, L, 16), dtype=np.float32))
+    mips_out = types.SimpleNamespace(mips_last_hidden_state=hid, memory_outputs=(mem,),
+                                     memory_attention_mask=torch.ones(B * K, L),
+                                     memory_input_ids=torch.zeros(B * K, L, dtype=torch.long))
+    ns = {"torch": torch, "query": query, "mips_out": mips_out, "query_batch_size": B}
+    exec(compile(code, str(rg), "exec"), ns)
+    np.savez_compressed(OUT / "doc_scores.npz", query=query[:, 0, :].numpy(), docs=hid[:, :, 0, :].numpy(),
+                        mips_scores=ns["mips_scores"].numpy(), memory_bias=ns["memory_bias"].numpy(),
+                        memory_seq_len=np.int64(L))
+    (OUT / "doc_scores_statements.txt").write_text(
+        "# statements executed from /root/reference/sotasum/retriever_generator.py\n"
+        + "\n".join("# " + ln.split("=")[0].strip() for ln in code.splitlines() if "=" in ln and not ln.startswith(" ")))
+    print("golden fixtures written to", OUT)
+    for f in sorted(OUT.glob("*.npz")):
+        print(f"  {f.name}: {f.stat().st_size/1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

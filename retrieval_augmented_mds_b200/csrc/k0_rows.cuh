@@ -1,0 +1,83 @@
+// k0_rows.cuh — K0: row ingest kernel (bank append and query preparation).
+//
+// One pass over fp32 rows [n, d]: optional L2 normalisation, cast to the storage type,
+// zero padding to d_pad, |row|^2 of the stored values, and a running max of the ORIGINAL
+// |row|^2. Fuses what the reference does in three host passes over the bank in
+// Mips.build_index (sotasum/mips.py:298-331: _map_norm :347-349, _map_normalize :358-361 ->
+// faiss.normalize_L2 :524, get_phi :55-56) and, for queries, Mips._prepare_query (:368-375).
+//
+// HBM-bound: algorithmic bytes per row = 4*d read + sizeof(T)*d_pad + 4 written.
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// grid: ceil(n_pad / 8) blocks of 256 threads (8 warps, one row per warp).
+// Rows [n, n_pad) of `out` are zero-filled (query tiles are padded to 128 rows).
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_rows_kernel(const float* x, int64_t n,
+                                                          int64_t n_pad, int d, int d_pad,
+                                                          int normalize, T* out,  // may alias x (in place)
+                                                          float* __restrict__ norm2_out,
+                                                          unsigned int* __restrict__ max_norm2_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  T* dst = out + row * d_pad;
+  if (row >= n) {
+    for (int i = lane; i < d_pad; i += 32) dst[i] = from_f32<T>(0.f);
+    if (norm2_out) {
+      if (lane == 0) norm2_out[row] = 0.f;
+    }
+    return;
+  }
+  const float* src = x + row * d;
+  float ss = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = src[i];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  // faiss.normalize_L2: x *= 1/sqrt(|x|^2), rows with zero norm are left untouched.
+  const float scale = (normalize && ss > 0.f) ? (1.0f / sqrtf(ss)) : 1.0f;
+  float ss_stored = 0.f;
+  for (int i = lane; i < d_pad; i += 32) {
+    float v = 0.f;
+    if (i < d) v = src[i] * scale;
+    const T t = from_f32<T>(v);
+    dst[i] = t;
+    const float r = to_f32<T>(t);
+    ss_stored = fmaf(r, r, ss_stored);
+  }
+  ss_stored = warp_sum(ss_stored);
+  if (lane == 0) {
+    if (norm2_out) norm2_out[row] = ss_stored;
+    // non-negative floats order like their bit patterns
+    if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(ss));
+  }
+}
+
+// Copy stored rows back as fp32 [n, d] (Mips.save / np_search support).
+template <typename T>
+__global__ void __launch_bounds__(256) reconstruct_rows_kernel(const T* __restrict__ bank,
+                                                               int64_t row0, int64_t n, int d,
+                                                               int d_pad, float* __restrict__ out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n * d) return;
+  const int64_t r = idx / d;
+  const int c = static_cast<int>(idx - r * d);
+  out[idx] = to_f32<T>(bank[(row0 + r) * d_pad + c]);
+}
+
+// ignore ids (global int64) -> local int32 row or -1 (not in this shard).
+__global__ void ignore_to_local_kernel(const int64_t* __restrict__ ignore_ids, int nq,
+                                       int64_t id_offset, int64_t ntotal, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int64_t l = ignore_ids[i] - id_offset;
+  out[i] = (l >= 0 && l < ntotal) ? static_cast<int>(l) : -1;
+}

@@ -1,0 +1,286 @@
+// k1_tc.cuh — K1 (tensor-core variant): sm_100a tcgen05/TMEM/TMA query x bank contraction with a
+// fused per-query top-k epilogue. Replaces the arithmetic of faiss.IndexFlat*.search as reached
+// from Mips.search (reference sotasum/mips.py:383-386) and of inner_product (mips.py:552-560).
+//
+// Mapping (one CTA per SM, persistent over its slice of the bank):
+//   * 128 queries per CTA = the 128 TMEM lanes. The query tile is STATIONARY: it is written once
+//     into TMEM columns [128, 128 + d_pad/2) as packed bf16 pairs and used as the A operand
+//     (tcgen05.mma with A in TMEM), so the only streamed operand is the bank.
+//   * bank rows stream HBM/L2 -> shared memory by TMA (64 rows x 64 k boxes, 128-byte swizzle),
+//     4 boxes (one 256-wide k slab) per pipeline stage, NUM_STAGES-deep mbarrier ring.
+//   * scores for 64 bank rows accumulate in one of two 64-column fp32 TMEM accumulators
+//     (M=128, N=64, K=16 instructions); the MMA of tile t+1 overlaps the epilogue of tile t.
+//   * epilogue: thread <-> query. Each thread pulls its lane's 64 scores (tcgen05.ld 32x32b),
+//     releases the accumulator, takes one max over them and compares with its running k-th best;
+//     only when something beats it (rare after warm-up) does it walk the 64 values and insert
+//     into its sorted list in shared memory. The [nq, N] score matrix never reaches HBM.
+//
+// Grid = n_qtiles * n_splits CTAs (<= #SMs): CTA (qtile, split) scans bank tiles
+// [split*T/S, (split+1)*T/S) for query tile qtile; CTAs of one split run side by side so a bank
+// tile is fetched from HBM once and served from L2 to the other query tiles.
+//
+// Roofline: tensor bound, 2*128*64*d_pad flops per tile; HBM bytes = one pass over
+// the bank per batch of <= 128*n_qtiles queries.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace tc {
+constexpr int BLOCK_M = 128;                          // queries per CTA (TMEM lanes)
+constexpr int ACC_N = 64;                             // bank rows per accumulator
+constexpr int KCH = 64;                               // bf16 per 128-byte swizzle row
+constexpr int BOX_BYTES = ACC_N * KCH * 2;            // 8 KiB: one TMA box
+constexpr int STAGE_KCH = 4;                          // boxes (k chunks) per stage
+constexpr int STAGE_BYTES = STAGE_KCH * BOX_BYTES;    // 32 KiB
+constexpr int TMEM_COLS = 512;
+constexpr int Q_COL0 = 2 * ACC_N;                     // query tile starts after the accumulators
+constexpr int MAX_DPAD = (TMEM_COLS - Q_COL0) * 2;    // 768
+constexpr int THREADS = 192;                          // 4 epilogue warps + TMA warp + MMA warp
+constexpr int MAX_STAGES = 6;
+constexpr int SMEM_LIMIT = 232448;                    // 227 KiB opt-in maximum
+
+// shared memory: [align pad 1024][stages][lists][barriers]
+__host__ __device__ inline int list_bytes(int k) { return BLOCK_M * k * 8; }
+__host__ __device__ inline int bar_bytes() { return (2 * MAX_STAGES + 6) * 8; }
+inline int pick_stages(int k) {
+  int s = (SMEM_LIMIT - 1024 - list_bytes(k) - bar_bytes()) / STAGE_BYTES;
+  return s > MAX_STAGES ? MAX_STAGES : s;
+}
+inline size_t smem_bytes(int k, int stages) {
+  return 1024 + static_cast<size_t>(stages) * STAGE_BYTES + list_bytes(k) + bar_bytes();
+}
+
+struct Params {
+  const __nv_bfloat16* q;   // [n_qtiles*128, d_pad] prepared queries (zero padded)
+  const float* xnorm2;      // [ntotal] (L2 only)
+  const int* ignore_local;  // [nq] or null
+  float* part_key;          // [n_splits, nq, k]
+  int* part_ids;
+  int64_t ntotal;
+  int nq, d_pad, k, n_tiles, n_qtiles, n_splits, stages;
+  unsigned long long cache_hint;
+};
+
+template <bool kL2>
+__global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
+    const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;   // 128B swizzle atoms need 1024B alignment
+  uint8_t* gen = smem_raw + (base - raw_addr);
+
+  const int S = p.stages;
+  const uint32_t lists_off = static_cast<uint32_t>(S) * STAGE_BYTES;
+  float* list_key = reinterpret_cast<float*>(gen + lists_off);
+  int* list_id = reinterpret_cast<int*>(gen + lists_off + BLOCK_M * p.k * 4);
+  const uint32_t bars = base + lists_off + list_bytes(p.k);
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (MAX_STAGES + i); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t qready_bar = bars + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 5);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + lists_off + list_bytes(p.k) + 8 * (2 * MAX_STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x % p.n_qtiles, split = blockIdx.x / p.n_qtiles;
+  const int tile0 = static_cast<int>(static_cast<int64_t>(split) * p.n_tiles / p.n_splits);
+  const int tile1 = static_cast<int>(static_cast<int64_t>(split + 1) * p.n_tiles / p.n_splits);
+  const int n_kch = p.d_pad / KCH;
+  const int n_kstages = (n_kch + STAGE_KCH - 1) / STAGE_KCH;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap);
+    for (int i = 0; i < S; ++i) {
+      ptx::mbar_init(full_bar(i), 1);    // producer's arrive.expect_tx
+      ptx::mbar_init(empty_bar(i), 1);   // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);          // tcgen05.commit
+      ptx::mbar_init(tempty_bar(a), BLOCK_M);   // every epilogue thread
+    }
+    ptx::mbar_init(qready_bar, BLOCK_M);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        const int row0 = tile * ACC_N;
+        for (int ks = 0; ks < n_kstages; ++ks) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const int nk = min(STAGE_KCH, n_kch - ks * STAGE_KCH);
+          ptx::mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(nk) * BOX_BYTES);
+          const uint32_t dst = base + static_cast<uint32_t>(stage) * STAGE_BYTES;
+          for (int c = 0; c < nk; ++c)
+            ptx::tma_load_2d_hint(dst + c * BOX_BYTES, &tmap, full_bar(stage),
+                                  (ks * STAGE_KCH + c) * KCH, row0, p.cache_hint);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, ACC_N);
+      ptx::mbar_wait(qready_bar, 0);
+      ptx::tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = tile0; tile < tile1; ++tile, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_N;
+        for (int ks = 0; ks < n_kstages; ++ks) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const int nk = min(STAGE_KCH, n_kch - ks * STAGE_KCH);
+          const uint32_t sbase = base + static_cast<uint32_t>(stage) * STAGE_BYTES;
+          const uint32_t a_tmem0 = tmem_base + Q_COL0 + ks * (STAGE_KCH * KCH / 2);
+#pragma unroll
+          for (int c = 0; c < STAGE_KCH; ++c) {
+            if (c < nk) {
+              const uint64_t bdesc = ptx::smem_desc_sw128(sbase + c * BOX_BYTES);
+#pragma unroll
+              for (int j = 0; j < KCH / 16; ++j) {
+                // 16 k per instruction: 8 TMEM columns of A, 32 bytes along the swizzled row of B
+                ptx::mma_bf16_ts(d_tmem, a_tmem0 + c * (KCH / 2) + j * 8, bdesc + 2u * j, idesc,
+                                 (ks | c | j) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          ptx::mma_commit(empty_bar(stage));   // frees the stage once these MMAs have read it
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::mma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (thread <-> query) =====================
+    const int row = warp * 32 + lane;
+    const int qrow = qtile * BLOCK_M + row;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+    // query tile -> TMEM (A operand, K-major: column c of lane m holds k = 2c, 2c+1)
+    {
+      const uint4* qsrc = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(qrow) * p.d_pad);
+      for (int c = 0; c < p.d_pad / 16; ++c) {
+        const uint4 a = qsrc[2 * c], b = qsrc[2 * c + 1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        ptx::tmem_st_x8(lane_addr + Q_COL0 + c * 8, v);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(qready_bar);
+    }
+
+    float* lk = list_key + row * p.k;
+    int* li = list_id + row * p.k;
+    for (int i = 0; i < p.k; ++i) {
+      lk[i] = -CUDART_INF_F;
+      li[i] = -1;
+    }
+    const bool live = qrow < p.nq;
+    const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
+    float thr = -CUDART_INF_F;
+
+    int it = 0;
+    for (int tile = tile0; tile < tile1; ++tile, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent insert path
+      ptx::tc_fence_after();
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_x32(lane_addr + acc * ACC_N, v0);
+      ptx::tmem_ld_x32(lane_addr + acc * ACC_N + 32, v1);
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar(acc));   // accumulator is in registers: MMA may reuse it
+
+      const int id0 = tile * ACC_N;
+      if (kL2) {
+        // ranking key for L2: <q,x> - |x|^2/2 (same for every lane: broadcast loads)
+        const float4* xn = reinterpret_cast<const float4*>(p.xnorm2 + id0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(xn + j);
+          v0[4 * j + 0] = __float_as_uint(__uint_as_float(v0[4 * j + 0]) - 0.5f * t.x);
+          v0[4 * j + 1] = __float_as_uint(__uint_as_float(v0[4 * j + 1]) - 0.5f * t.y);
+          v0[4 * j + 2] = __float_as_uint(__uint_as_float(v0[4 * j + 2]) - 0.5f * t.z);
+          v0[4 * j + 3] = __float_as_uint(__uint_as_float(v0[4 * j + 3]) - 0.5f * t.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(xn + 8 + j);
+          v1[4 * j + 0] = __float_as_uint(__uint_as_float(v1[4 * j + 0]) - 0.5f * t.x);
+          v1[4 * j + 1] = __float_as_uint(__uint_as_float(v1[4 * j + 1]) - 0.5f * t.y);
+          v1[4 * j + 2] = __float_as_uint(__uint_as_float(v1[4 * j + 2]) - 0.5f * t.z);
+          v1[4 * j + 3] = __float_as_uint(__uint_as_float(v1[4 * j + 3]) - 0.5f * t.w);
+        }
+      }
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        m = fmaxf(m, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+      if (m > thr && live) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v0[j]);
+          if (s > thr) {
+            const int id = id0 + j;
+            if (id < p.ntotal && id != ign) thr = topk_list_insert(lk, li, p.k, s, id);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v1[j]);
+          if (s > thr) {
+            const int id = id0 + 32 + j;
+            if (id < p.ntotal && id != ign) thr = topk_list_insert(lk, li, p.k, s, id);
+          }
+        }
+      }
+    }
+
+    if (live) {
+      const size_t o = (static_cast<size_t>(split) * p.nq + qrow) * p.k;
+      for (int i = 0; i < p.k; ++i) {
+        p.part_key[o + i] = lk[i];
+        p.part_ids[o + i] = li[i];
+      }
+    }
+  }
+
+  // teardown: every MMA has completed (the epilogue consumed the last accumulator)
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+}  // namespace tc

@@ -1,0 +1,168 @@
+// k2_merge.cuh — K2: k-way merge of per-split / per-rank candidate lists, one warp per query.
+//
+// Selection is "k_out rounds of warp arg-max under a strictly-after constraint": round j picks
+// the best candidate that comes strictly after round j-1's pick in the total order
+// (key descending, id ascending). No scratch, no mutation of the inputs, deterministic for
+// any number of parts (shard-count invariant), and the ignore filter of Mips.search
+// (reference sotasum/mips.py:388-398: drop the hit whose id == ignore_indexes[j]) is a skip.
+//
+// LOCAL = true : candidates carry int32 shard-local rows; output is still the ranking key,
+//                ids become global (id_offset + row) and |x|^2 is gathered from the shard.
+// LOCAL = false: candidates carry int64 global ids (+ optional |x|^2); output goes through the
+//                metric transform and the doc-score arithmetic of
+//                retriever_generator.py:158-193 (cosine, per-doc softmax, memory_bias).
+#pragma once
+#include "common.cuh"
+#include "mips_b200.h"
+
+struct MergeBest {
+  float key;
+  int64_t id;
+  int pos;
+};
+
+__device__ __forceinline__ bool merge_better(float ka, int64_t ia, float kb, int64_t ib) {
+  return (ka > kb) || (ka == kb && ia < ib);
+}
+
+template <bool LOCAL>
+__global__ void __launch_bounds__(128) merge_topk_kernel(
+    const float* __restrict__ cand_key, const void* __restrict__ cand_ids_v,
+    const float* __restrict__ cand_xn2,   // !LOCAL: [n_parts, nq, k_in] or null
+    const float* __restrict__ bank_xn2,   // LOCAL: shard norm array
+    int n_parts, int nq, int k_in, int k_out, int64_t id_offset,
+    const int64_t* __restrict__ ignore_ids, int metric, int out_mode, float phi,
+    const float* __restrict__ q_norm2, float* __restrict__ out_key, int64_t* __restrict__ out_ids,
+    float* __restrict__ out_xn2, float* __restrict__ cosine, float* __restrict__ doc_prob,
+    float beta, float beta_bias, float* __restrict__ memory_bias, int mem_len) {
+  __shared__ float s_key[4][MIPS_MAX_K];
+  __shared__ float s_xn2[4][MIPS_MAX_K];
+  __shared__ float s_cos[4][MIPS_MAX_K];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= nq) return;
+
+  const int32_t* ids32 = static_cast<const int32_t*>(cand_ids_v);
+  const int64_t* ids64 = static_cast<const int64_t*>(cand_ids_v);
+  const int64_t ign = ignore_ids ? ignore_ids[q] : -1;
+  const int C = n_parts * k_in;
+
+  float prev_key = CUDART_INF_F;
+  int64_t prev_id = -1;
+  int n_found = 0;
+  for (int j = 0; j < k_out; ++j) {
+    MergeBest b{-CUDART_INF_F, INT64_MAX, -1};
+    for (int c = lane; c < C; c += 32) {
+      const int p = c / k_in, s = c - p * k_in;
+      const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + s;
+      int64_t id;
+      if (LOCAL) {
+        const int32_t l = ids32[a];
+        id = l < 0 ? -1 : id_offset + l;
+      } else {
+        id = ids64[a];
+      }
+      if (id < 0 || id == ign) continue;
+      const float key = cand_key[a];
+      const bool after = (key < prev_key) || (key == prev_key && id > prev_id);
+      if (!after) continue;
+      if (merge_better(key, id, b.key, b.id)) {
+        b.key = key;
+        b.id = id;
+        b.pos = static_cast<int>(a);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, b.key, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, b.id, o);
+      const int op = __shfl_xor_sync(0xffffffffu, b.pos, o);
+      if (op >= 0 && (b.pos < 0 || merge_better(ok, oi, b.key, b.id))) {
+        b.key = ok;
+        b.id = oi;
+        b.pos = op;
+      }
+    }
+    if (b.pos < 0) break;
+    prev_key = b.key;
+    prev_id = b.id;
+    n_found = j + 1;
+    if (lane == 0) {
+      float xn = 0.f;
+      if (LOCAL) {
+        if (bank_xn2) xn = bank_xn2[b.id - id_offset];
+      } else {
+        if (cand_xn2) xn = cand_xn2[b.pos];
+      }
+      s_key[w][j] = b.key;
+      s_xn2[w][j] = xn;
+      out_ids[static_cast<size_t>(q) * k_out + j] = b.id;
+    }
+  }
+  __syncwarp();
+
+  const float qn2 = q_norm2 ? q_norm2[q] : 0.f;
+  float lmax = -CUDART_INF_F;
+  for (int j = lane; j < k_out; j += 32) {
+    const size_t o = static_cast<size_t>(q) * k_out + j;
+    if (j >= n_found) {
+      out_ids[o] = -1;
+      if (LOCAL) {
+        out_key[o] = -CUDART_INF_F;
+        if (out_xn2) out_xn2[o] = 0.f;
+      } else {
+        out_key[o] = (out_mode == MIPS_OUT_IP) ? -CUDART_INF_F : CUDART_INF_F;
+        if (cosine) cosine[o] = 0.f;
+      }
+      s_cos[w][j] = -CUDART_INF_F;
+      continue;
+    }
+    const float key = s_key[w][j], xn = s_xn2[w][j];
+    if (LOCAL) {
+      out_key[o] = key;
+      if (out_xn2) out_xn2[o] = xn;
+      continue;
+    }
+    // ranking key -> inner product
+    const float ip = (metric == MIPS_METRIC_L2) ? key + 0.5f * xn : key;
+    float dval;
+    if (out_mode == MIPS_OUT_IP) {
+      dval = ip;
+    } else if (out_mode == MIPS_OUT_L2) {
+      dval = fmaxf(qn2 + xn - 2.f * ip, 0.f);
+    } else {
+      dval = qn2 + phi - 2.f * ip;
+    }
+    out_key[o] = dval;
+    // retriever_generator.py:159-172: <q,d> / (|q| |d|)
+    const float den = sqrtf(qn2) * sqrtf(xn);
+    const float cs = den > 0.f ? ip / den : 0.f;
+    if (cosine) cosine[o] = cs;
+    s_cos[w][j] = cs;
+    lmax = fmaxf(lmax, beta * cs + beta_bias);
+  }
+  if (LOCAL) return;
+  __syncwarp();
+
+  if (doc_prob) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    float lsum = 0.f;
+    for (int j = lane; j < n_found; j += 32) lsum += __expf(beta * s_cos[w][j] + beta_bias - lmax);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    for (int j = lane; j < k_out; j += 32) {
+      const size_t o = static_cast<size_t>(q) * k_out + j;
+      doc_prob[o] = j < n_found ? __expf(beta * s_cos[w][j] + beta_bias - lmax) / lsum : 0.f;
+    }
+  }
+  if (memory_bias) {
+    // retriever_generator.py:188-192: bias[q, j*L + t] = cosine[q, j]
+    const int total = k_out * mem_len;
+    float* dst = memory_bias + static_cast<size_t>(q) * total;
+    for (int t = lane; t < total; t += 32) {
+      const int j = t / mem_len;
+      dst[t] = j < n_found ? s_cos[w][j] : 0.f;
+    }
+  }
+}

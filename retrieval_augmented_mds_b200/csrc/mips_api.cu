@@ -1,0 +1,637 @@
+// mips_api.cu — host side of the C ABI declared in include/mips_b200.h.
+// Owns the HBM bank shard, the norm array and the scratch buffers; enqueues K0 (ingest),
+// K1 (search, tcgen05 or SIMT) and K2 (merge) on the caller's stream. No CPU compute path:
+// every entry point that searches launches CUDA kernels or fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "k0_rows.cuh"
+#include "k1_simt.cuh"
+#include "k1_tc.cuh"
+#include "k2_merge.cuh"
+#include "mips_b200.h"
+
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return set_err(_e == cudaErrorMemoryAllocation ? MIPS_E_NOMEM : MIPS_E_CUDA, "%s: %s (%s:%d)", \
+                     #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                   \
+  do {                                                                                       \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return set_err(MIPS_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e));            \
+  } while (0)
+
+constexpr int kProfSlots = 256;
+
+struct mips_index_s {
+  int d = 0, d_pad = 0, metric = 0, dtype = 0, device = 0;
+  int64_t ntotal = 0, capacity = 0;
+  void* bank = nullptr;
+  float* norm2 = nullptr;
+  unsigned int* max_norm2_bits = nullptr;  // device scalar
+  float phi = 0.f;
+  int sm_count = 148;
+  // TMA descriptor of the bank (re-encoded when the allocation changes)
+  CUtensorMap tmap;
+  bool tmap_valid = false;
+  // scratch (grown on demand; stable after warm-up)
+  void* q_prep = nullptr;      size_t q_prep_bytes = 0;
+  float* q_norm2 = nullptr;    size_t q_norm2_bytes = 0;
+  float* part_key = nullptr;   size_t part_key_bytes = 0;
+  int* part_ids = nullptr;     size_t part_ids_bytes = 0;
+  int* ign_local = nullptr;    size_t ign_bytes = 0;
+  float* stage_x = nullptr;    size_t stage_x_bytes = 0;
+  // host-call scratch
+  float* hq = nullptr;         size_t hq_bytes = 0;
+  int64_t* hign = nullptr;     size_t hign_bytes = 0;
+  float* hkey = nullptr;       size_t hkey_bytes = 0;
+  int64_t* hids = nullptr;     size_t hids_bytes = 0;
+  float* hxn2 = nullptr;       size_t hxn2_bytes = 0;
+  float* hqn2 = nullptr;       size_t hqn2_bytes = 0;
+  float* hD = nullptr;         size_t hD_bytes = 0;
+  int64_t* hI = nullptr;       size_t hI_bytes = 0;
+  // profiling
+  int profiling = 0;
+  cudaEvent_t ev0[kProfSlots], ev1[kProfSlots];
+  int prof_n = 0;
+  bool prof_events = false;
+  const char* last_algo = "none";
+  bool attrs_set = false;
+};
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+  static encode_tiled_fn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<encode_tiled_fn>(p);
+  return fn;
+}
+
+template <typename P>
+static int grow(P** ptr, size_t* cur, size_t need) {
+  if (need <= *cur) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *cur = 0;
+  size_t bytes = std::max(need, static_cast<size_t>(256));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(ptr), bytes));
+  *cur = bytes;
+  return 0;
+}
+
+static size_t elem_bytes(const mips_index_s* h) { return h->dtype == MIPS_DTYPE_BF16 ? 2 : 4; }
+
+static int encode_bank_tmap(mips_index_s* h) {
+  h->tmap_valid = false;
+  if (h->dtype != MIPS_DTYPE_BF16 || h->d_pad > tc::MAX_DPAD) return 0;
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->d_pad), static_cast<cuuint64_t>(h->capacity)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(h->d_pad) * 2};
+  const cuuint32_t box[2] = {tc::KCH, tc::ACC_N};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->bank, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  h->tmap_valid = true;
+  return 0;
+}
+
+// (re)allocate the shard to hold at least `rows`; preserves existing rows.
+static int ensure_capacity(mips_index_s* h, int64_t rows, cudaStream_t st) {
+  if (rows <= h->capacity) return 0;
+  int64_t cap = std::max<int64_t>(rows, h->capacity * 2);
+  cap = std::max<int64_t>(round_up_l(cap, kRowAlign), 1024);
+  void* nb = nullptr;
+  float* nn = nullptr;
+  const size_t row_bytes = static_cast<size_t>(h->d_pad) * elem_bytes(h);
+  CUDA_TRY(cudaMalloc(&nb, static_cast<size_t>(cap) * row_bytes));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&nn), static_cast<size_t>(cap) * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(nb);
+    return set_err(MIPS_E_NOMEM, "cudaMalloc norm array: %s", cudaGetErrorString(e));
+  }
+  if (h->ntotal > 0) {
+    CUDA_TRY(cudaMemcpyAsync(nb, h->bank, static_cast<size_t>(h->ntotal) * row_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(nn, h->norm2, static_cast<size_t>(h->ntotal) * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+  }
+  // rows beyond ntotal must hold finite values: they are multiplied (and masked) by K1
+  CUDA_TRY(cudaMemsetAsync(static_cast<uint8_t*>(nb) + static_cast<size_t>(h->ntotal) * row_bytes, 0,
+                           static_cast<size_t>(cap - h->ntotal) * row_bytes, st));
+  CUDA_TRY(cudaMemsetAsync(nn + h->ntotal, 0, static_cast<size_t>(cap - h->ntotal) * sizeof(float), st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h->bank) cudaFree(h->bank);
+  if (h->norm2) cudaFree(h->norm2);
+  h->bank = nb;
+  h->norm2 = nn;
+  h->capacity = cap;
+  return encode_bank_tmap(h);
+}
+
+static int set_kernel_attrs(mips_index_s* h) {
+  if (h->attrs_set) return 0;
+  const int simt_max = static_cast<int>(simt::smem_bytes(16));
+  CUDA_TRY(cudaFuncSetAttribute(simt::search_simt_kernel<float, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, simt_max));
+  CUDA_TRY(cudaFuncSetAttribute(simt::search_simt_kernel<float, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, simt_max));
+  CUDA_TRY(cudaFuncSetAttribute(simt::search_simt_kernel<__nv_bfloat16, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, simt_max));
+  CUDA_TRY(cudaFuncSetAttribute(simt::search_simt_kernel<__nv_bfloat16, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, simt_max));
+  CUDA_TRY(cudaFuncSetAttribute(tc::search_tc_kernel<false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+  CUDA_TRY(cudaFuncSetAttribute(tc::search_tc_kernel<true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+  h->attrs_set = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mips_last_error(void) { return g_err; }
+int64_t mips_launch_count(void) { return g_launches.load(); }
+
+int mips_create(mips_handle* out, int d, int metric, int dtype, int device, int64_t capacity_rows) {
+  if (!out) return set_err(MIPS_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (d <= 0 || d > 65536) return set_err(MIPS_E_INVALID, "d must be in [1, 65536], got %d", d);
+  if (metric != MIPS_METRIC_IP && metric != MIPS_METRIC_L2)
+    return set_err(MIPS_E_INVALID, "metric must be 0 (inner product) or 1 (L2), got %d", metric);
+  if (dtype != MIPS_DTYPE_F32 && dtype != MIPS_DTYPE_BF16)
+    return set_err(MIPS_E_INVALID, "dtype must be 0 (fp32) or 1 (bf16), got %d", dtype);
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev)
+    return set_err(MIPS_E_INVALID, "device %d out of range (%d CUDA devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_err(MIPS_E_UNSUPPORTED, "built for sm_100a only; device %d is sm_%d%d", device,
+                   prop.major, prop.minor);
+  mips_index_s* h = new (std::nothrow) mips_index_s();
+  if (!h) return set_err(MIPS_E_NOMEM, "host allocation failed");
+  h->d = d;
+  h->d_pad = round_up_i(d, kDimAlign);
+  h->metric = metric;
+  h->dtype = dtype;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->max_norm2_bits), sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->max_norm2_bits, 0, sizeof(unsigned int));
+  if (e != cudaSuccess) {
+    delete h;
+    return set_err(MIPS_E_CUDA, "cudaMalloc stats: %s", cudaGetErrorString(e));
+  }
+  int rc = set_kernel_attrs(h);
+  if (rc == 0 && capacity_rows > 0) rc = ensure_capacity(h, capacity_rows, nullptr);
+  if (rc != 0) {
+    mips_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int mips_destroy(mips_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  void* dev[] = {h->bank, h->norm2, h->max_norm2_bits, h->q_prep, h->q_norm2, h->part_key,
+                 h->part_ids, h->ign_local, h->stage_x, h->hq, h->hign, h->hkey, h->hids,
+                 h->hxn2, h->hqn2, h->hD, h->hI};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  if (h->prof_events)
+    for (int i = 0; i < kProfSlots; ++i) {
+      cudaEventDestroy(h->ev0[i]);
+      cudaEventDestroy(h->ev1[i]);
+    }
+  delete h;
+  return 0;
+}
+
+int mips_reset(mips_handle h) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->ntotal = 0;
+  h->phi = 0.f;
+  CUDA_TRY(cudaMemset(h->max_norm2_bits, 0, sizeof(unsigned int)));
+  return 0;
+}
+
+int64_t mips_ntotal(mips_handle h) { return h ? h->ntotal : -1; }
+int mips_dim(mips_handle h) { return h ? h->d : -1; }
+int mips_metric(mips_handle h) { return h ? h->metric : -1; }
+int mips_dtype(mips_handle h) { return h ? h->dtype : -1; }
+int mips_set_phi(mips_handle h, float phi) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  h->phi = phi;
+  return 0;
+}
+float mips_get_phi(mips_handle h) { return h ? h->phi : 0.f; }
+const char* mips_last_algo(mips_handle h) { return h ? h->last_algo : "none"; }
+
+int mips_set_profiling(mips_handle h, int on) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (on && !h->prof_events) {
+    for (int i = 0; i < kProfSlots; ++i) {
+      CUDA_TRY(cudaEventCreate(&h->ev0[i]));
+      CUDA_TRY(cudaEventCreate(&h->ev1[i]));
+    }
+    h->prof_events = true;
+  }
+  h->profiling = on;
+  h->prof_n = 0;
+  return 0;
+}
+
+// Sum of the K1 launch durations (ms) recorded since profiling was (re)enabled; *n_launches
+// receives how many launches that covers. Sync on the recorded events.
+float mips_k1_ms_total(mips_handle h) {
+  if (!h || !h->prof_events || h->prof_n == 0) return -1.f;
+  float total = 0.f;
+  const int n = std::min(h->prof_n, kProfSlots);
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->ev1[i]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0[i], h->ev1[i]) != cudaSuccess) return -1.f;
+    total += ms;
+  }
+  return total;
+}
+int mips_prof_count(mips_handle h) { return h ? std::min(h->prof_n, kProfSlots) : 0; }
+
+// ------------------------------------------------------------------------------------------ K0
+static int launch_ingest(mips_index_s* h, const float* x_dev, int64_t n, int64_t n_pad, int normalize,
+                         void* out, float* norm2_out, unsigned int* maxbits, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>((n_pad + 7) / 8);
+  if (blocks == 0) return 0;
+  if (h->dtype == MIPS_DTYPE_BF16)
+    ingest_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+        x_dev, n, n_pad, h->d, h->d_pad, normalize, static_cast<__nv_bfloat16*>(out), norm2_out, maxbits);
+  else
+    ingest_rows_kernel<float><<<blocks, 256, 0, st>>>(x_dev, n, n_pad, h->d, h->d_pad, normalize,
+                                                      static_cast<float*>(out), norm2_out, maxbits);
+  LAUNCH_CHECK("ingest_rows_kernel");
+  return 0;
+}
+
+int mips_add(mips_handle h, const float* x, int64_t n, int x_on_device, int normalize, void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (n < 0 || (n > 0 && !x)) return set_err(MIPS_E_INVALID, "bad x / n");
+  if (n == 0) return 0;
+  if (h->ntotal + n > (static_cast<int64_t>(1) << 31) - 64)
+    return set_err(MIPS_E_UNSUPPORTED, "shard limited to 2^31-64 rows (int32 local ids)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_capacity(h, h->ntotal + n, st);
+  if (rc) return rc;
+  const size_t eb = elem_bytes(h);
+  if (x_on_device) {
+    void* dst = static_cast<uint8_t*>(h->bank) + static_cast<size_t>(h->ntotal) * h->d_pad * eb;
+    rc = launch_ingest(h, x, n, n, normalize, dst, h->norm2 + h->ntotal, h->max_norm2_bits, st);
+    if (rc) return rc;
+    h->ntotal += n;
+    return 0;
+  }
+  // host rows: stage through a device buffer in <= 64 MiB chunks (stream ordered)
+  const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(h->d) * 4));
+  rc = grow(&h->stage_x, &h->stage_x_bytes,
+            static_cast<size_t>(std::min(chunk_rows, n)) * h->d * sizeof(float));
+  if (rc) return rc;
+  for (int64_t r = 0; r < n; r += chunk_rows) {
+    const int64_t m = std::min(chunk_rows, n - r);
+    CUDA_TRY(cudaMemcpyAsync(h->stage_x, x + r * h->d, static_cast<size_t>(m) * h->d * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    void* dst = static_cast<uint8_t*>(h->bank) + static_cast<size_t>(h->ntotal) * h->d_pad * eb;
+    rc = launch_ingest(h, h->stage_x, m, m, normalize, dst, h->norm2 + h->ntotal, h->max_norm2_bits, st);
+    if (rc) return rc;
+    h->ntotal += m;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mips_normalize_l2(float* x, int64_t n, int d, int x_on_device, int device, void* stream) {
+  if (n < 0 || d <= 0 || (n > 0 && !x)) return set_err(MIPS_E_INVALID, "bad x / n / d");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* buf = x;
+  const size_t bytes = static_cast<size_t>(n) * d * sizeof(float);
+  if (!x_on_device) {
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&buf), bytes));
+    cudaError_t e = cudaMemcpyAsync(buf, x, bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+      cudaFree(buf);
+      return set_err(MIPS_E_CUDA, "H2D: %s", cudaGetErrorString(e));
+    }
+  }
+  // in place: each warp reads its whole row before it rewrites it element by element
+  ingest_rows_kernel<float><<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(buf, n, n, d, d, 1, buf,
+                                                                             nullptr, nullptr);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && !x_on_device) {
+    e = cudaMemcpyAsync(x, buf, bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  if (!x_on_device) cudaFree(buf);
+  if (e != cudaSuccess) return set_err(MIPS_E_CUDA, "normalize_l2: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mips_max_norm2(mips_handle h, float* out, void* stream) {
+  if (!h || !out) return set_err(MIPS_E_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned int bits = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bits, h->max_norm2_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out, &bits, sizeof(float));
+  return 0;
+}
+
+int mips_reconstruct(mips_handle h, int64_t row0, int64_t n, float* out, int out_on_device, void* stream) {
+  if (!h || !out) return set_err(MIPS_E_INVALID, "null argument");
+  if (row0 < 0 || n < 0 || row0 + n > h->ntotal)
+    return set_err(MIPS_E_INVALID, "rows [%lld, %lld) outside [0, %lld)", (long long)row0,
+                   (long long)(row0 + n), (long long)h->ntotal);
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk_rows = out_on_device ? n : std::max<int64_t>(1, (64ll << 20) / (static_cast<int64_t>(h->d) * 4));
+  if (!out_on_device) {
+    int rc = grow(&h->stage_x, &h->stage_x_bytes,
+                  static_cast<size_t>(std::min(chunk_rows, n)) * h->d * sizeof(float));
+    if (rc) return rc;
+  }
+  for (int64_t r = 0; r < n; r += chunk_rows) {
+    const int64_t m = std::min(chunk_rows, n - r);
+    float* dst = out_on_device ? out + r * h->d : h->stage_x;
+    const int64_t total = m * h->d;
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    if (h->dtype == MIPS_DTYPE_BF16)
+      reconstruct_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(h->bank), row0 + r, m, h->d, h->d_pad, dst);
+    else
+      reconstruct_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(h->bank),
+                                                             row0 + r, m, h->d, h->d_pad, dst);
+    LAUNCH_CHECK("reconstruct_rows_kernel");
+    if (!out_on_device) {
+      CUDA_TRY(cudaMemcpyAsync(out + r * h->d, h->stage_x, static_cast<size_t>(total) * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ K1
+static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_normalize,
+                        const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
+                        int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, cudaStream_t st) {
+  int rc;
+  const size_t eb = elem_bytes(h);
+  const int nq_pad = round_up_i(nq, tc::BLOCK_M);
+  rc = grow(&h->q_prep, &h->q_prep_bytes, static_cast<size_t>(nq_pad) * h->d_pad * eb);
+  if (rc) return rc;
+  rc = grow(&h->q_norm2, &h->q_norm2_bytes, static_cast<size_t>(nq_pad) * sizeof(float));
+  if (rc) return rc;
+  // query preparation (_prepare_query, mips.py:368-375): normalise, cast, pad, |q|^2
+  rc = launch_ingest(h, q, nq, nq_pad, q_normalize, h->q_prep, h->q_norm2, nullptr, st);
+  if (rc) return rc;
+  if (out_qnorm2)
+    CUDA_TRY(cudaMemcpyAsync(out_qnorm2, h->q_norm2, static_cast<size_t>(nq) * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+  const int* ign_local = nullptr;
+  if (ignore_ids) {
+    rc = grow(&h->ign_local, &h->ign_bytes, static_cast<size_t>(nq) * sizeof(int));
+    if (rc) return rc;
+    ignore_to_local_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ignore_ids, nq, id_offset, h->ntotal,
+                                                             h->ign_local);
+    LAUNCH_CHECK("ignore_to_local_kernel");
+    ign_local = h->ign_local;
+  }
+
+  const bool l2 = h->metric == MIPS_METRIC_L2;
+  const bool use_tc = algo == MIPS_ALGO_TC;
+  int n_parts = 0;
+  const int slot = h->prof_n % kProfSlots;
+  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
+
+  if (use_tc) {
+    const int n_tiles = static_cast<int>((h->ntotal + tc::ACC_N - 1) / tc::ACC_N);
+    const int n_qtiles = nq_pad / tc::BLOCK_M;
+    int n_splits = std::max(1, std::min(h->sm_count / n_qtiles, n_tiles));
+    n_parts = n_splits;
+    const size_t pk = static_cast<size_t>(n_parts) * nq * k;
+    rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+    if (rc) return rc;
+    rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
+    if (rc) return rc;
+    tc::Params p;
+    p.q = static_cast<const __nv_bfloat16*>(h->q_prep);
+    p.xnorm2 = h->norm2;
+    p.ignore_local = ign_local;
+    p.part_key = h->part_key;
+    p.part_ids = h->part_ids;
+    p.ntotal = h->ntotal;
+    p.nq = nq;
+    p.d_pad = h->d_pad;
+    p.k = k;
+    p.n_tiles = n_tiles;
+    p.n_qtiles = n_qtiles;
+    p.n_splits = n_splits;
+    p.stages = tc::pick_stages(k);
+    // a bank tile is re-read by the other query tiles from L2; with one query tile it is dead
+    p.cache_hint = n_qtiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+    const size_t smem = tc::smem_bytes(k, p.stages);
+    const unsigned grid = static_cast<unsigned>(n_qtiles * n_splits);
+    if (l2)
+      tc::search_tc_kernel<true><<<grid, tc::THREADS, smem, st>>>(h->tmap, p);
+    else
+      tc::search_tc_kernel<false><<<grid, tc::THREADS, smem, st>>>(h->tmap, p);
+    LAUNCH_CHECK("search_tc_kernel");
+    h->last_algo = "tc";
+  } else {
+    const int n_tiles = static_cast<int>((h->ntotal + simt::BN - 1) / simt::BN);
+    const int n_qtiles = (nq + simt::BM - 1) / simt::BM;
+    const int target_blocks = 4 * h->sm_count;
+    int n_splits = std::max(1, std::min((target_blocks + n_qtiles - 1) / n_qtiles, n_tiles));
+    n_splits = std::min(n_splits, 65535);
+    const int nsub = simt::nsub_for_k(k);
+    n_parts = n_splits * nsub;
+    const size_t pk = static_cast<size_t>(n_parts) * nq * k;
+    rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+    if (rc) return rc;
+    rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
+    if (rc) return rc;
+    const dim3 grid(n_qtiles, n_splits);
+    const size_t smem = simt::smem_bytes(k);
+#define SIMT_LAUNCH(T, L2)                                                                         \
+  simt::search_simt_kernel<T, L2><<<grid, simt::THREADS, smem, st>>>(                              \
+      static_cast<const T*>(h->q_prep), static_cast<const T*>(h->bank), h->norm2, nq, h->ntotal,   \
+      h->d_pad, k, ign_local, n_tiles, h->part_key, h->part_ids)
+    if (h->dtype == MIPS_DTYPE_BF16) {
+      if (l2) SIMT_LAUNCH(__nv_bfloat16, true); else SIMT_LAUNCH(__nv_bfloat16, false);
+    } else {
+      if (l2) SIMT_LAUNCH(float, true); else SIMT_LAUNCH(float, false);
+    }
+#undef SIMT_LAUNCH
+    LAUNCH_CHECK("search_simt_kernel");
+    h->last_algo = "simt";
+  }
+  if (h->profiling) {
+    CUDA_TRY(cudaEventRecord(h->ev1[slot], st));
+    h->prof_n++;
+  }
+
+  // local k-way merge: split lists -> one list per query, global ids, |x|^2 gathered
+  merge_topk_kernel<true><<<(nq + 3) / 4, 128, 0, st>>>(
+      h->part_key, h->part_ids, nullptr, h->norm2, n_parts, nq, k, k, id_offset, nullptr, h->metric,
+      MIPS_OUT_IP, 0.f, nullptr, out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0);
+  LAUNCH_CHECK("merge_topk_kernel<local>");
+  return 0;
+}
+
+int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normalize,
+                      const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
+                      int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (nq < 0 || (nq > 0 && (!q || !out_key || !out_ids))) return set_err(MIPS_E_INVALID, "bad q / outputs");
+  if (k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "k must be in [1, %d], got %d", MIPS_MAX_K, k);
+  if (nq == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool tc_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc::MAX_DPAD && h->tmap_valid;
+  if (algo == MIPS_ALGO_AUTO) algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
+  if (algo == MIPS_ALGO_TC && !tc_ok)
+    return set_err(MIPS_E_UNSUPPORTED, "tensor-core search needs a bf16 bank with d_pad <= %d", tc::MAX_DPAD);
+  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_SIMT) return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
+  if (h->ntotal == 0) {
+    // faiss semantics on an empty index: ids -1
+    CUDA_TRY(cudaMemsetAsync(out_ids, 0xff, static_cast<size_t>(nq) * k * sizeof(int64_t), st));
+    merge_topk_kernel<true><<<(nq + 3) / 4, 128, 0, st>>>(
+        nullptr, nullptr, nullptr, nullptr, 0, nq, k, k, 0, nullptr, h->metric, MIPS_OUT_IP, 0.f, nullptr,
+        out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0);
+    LAUNCH_CHECK("merge_topk_kernel<empty>");
+    if (out_qnorm2) CUDA_TRY(cudaMemsetAsync(out_qnorm2, 0, static_cast<size_t>(nq) * sizeof(float), st));
+    return 0;
+  }
+  // bound the scratch: chunks of queries (one kernel launch each)
+  const int chunk = algo == MIPS_ALGO_TC ? h->sm_count * tc::BLOCK_M : 16384;
+  for (int q0 = 0; q0 < nq; q0 += chunk) {
+    const int m = std::min(chunk, nq - q0);
+    int rc = search_chunk(h, q + static_cast<size_t>(q0) * h->d, m, k, q_normalize,
+                          ignore_ids ? ignore_ids + q0 : nullptr, id_offset, algo,
+                          out_key + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k,
+                          out_xnorm2 ? out_xnorm2 + static_cast<size_t>(q0) * k : nullptr,
+                          out_qnorm2 ? out_qnorm2 + q0 : nullptr, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+int mips_merge(const float* cand_key, const int64_t* cand_ids, const float* cand_xnorm2, int n_parts,
+               int nq, int k_in, int k_out, int metric, int out_mode, float phi, const float* q_norm2,
+               const int64_t* ignore_ids, float* D, int64_t* I, float* cosine, float* doc_prob,
+               float beta, float beta_bias, float* memory_bias, int mem_len, void* stream) {
+  if (nq < 0 || n_parts < 0 || k_in < 1 || k_out < 1 || k_out > MIPS_MAX_K)
+    return set_err(MIPS_E_INVALID, "bad merge shape (n_parts=%d nq=%d k_in=%d k_out=%d)", n_parts, nq, k_in, k_out);
+  if (nq == 0) return 0;
+  if (!D || !I || (n_parts > 0 && (!cand_key || !cand_ids))) return set_err(MIPS_E_INVALID, "null buffers");
+  if (out_mode < MIPS_OUT_IP || out_mode > MIPS_OUT_AUGL2) return set_err(MIPS_E_INVALID, "bad out_mode %d", out_mode);
+  const bool need_xn2 = out_mode == MIPS_OUT_L2 || metric == MIPS_METRIC_L2 || cosine || doc_prob || memory_bias;
+  if (need_xn2 && n_parts > 0 && !cand_xnorm2) return set_err(MIPS_E_INVALID, "cand_xnorm2 required for L2 / cosine outputs");
+  if ((out_mode != MIPS_OUT_IP || cosine || doc_prob || memory_bias) && !q_norm2)
+    return set_err(MIPS_E_INVALID, "q_norm2 required for L2 / cosine outputs");
+  if (memory_bias && mem_len < 1) return set_err(MIPS_E_INVALID, "mem_len must be >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  merge_topk_kernel<false><<<(nq + 3) / 4, 128, 0, st>>>(
+      cand_key, cand_ids, cand_xnorm2, nullptr, n_parts, nq, k_in, k_out, 0, ignore_ids, metric, out_mode,
+      phi, q_norm2, D, I, nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len);
+  LAUNCH_CHECK("merge_topk_kernel<final>");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ e2e
+int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normalize,
+                     const int64_t* ignore_ids, int out_mode, float* D, int64_t* I, void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (nq < 0 || (nq > 0 && (!xq || !D || !I))) return set_err(MIPS_E_INVALID, "bad host buffers");
+  if (k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "k must be in [1, %d], got %d", MIPS_MAX_K, k);
+  if (nq == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nk = static_cast<size_t>(nq) * k;
+  int rc = 0;
+  if ((rc = grow(&h->hq, &h->hq_bytes, static_cast<size_t>(nq) * h->d * sizeof(float)))) return rc;
+  if ((rc = grow(&h->hkey, &h->hkey_bytes, nk * sizeof(float)))) return rc;
+  if ((rc = grow(&h->hids, &h->hids_bytes, nk * sizeof(int64_t)))) return rc;
+  if ((rc = grow(&h->hxn2, &h->hxn2_bytes, nk * sizeof(float)))) return rc;
+  if ((rc = grow(&h->hqn2, &h->hqn2_bytes, static_cast<size_t>(nq) * sizeof(float)))) return rc;
+  if ((rc = grow(&h->hD, &h->hD_bytes, nk * sizeof(float)))) return rc;
+  if ((rc = grow(&h->hI, &h->hI_bytes, nk * sizeof(int64_t)))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->hq, xq, static_cast<size_t>(nq) * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int64_t* ign_dev = nullptr;
+  if (ignore_ids) {
+    if ((rc = grow(&h->hign, &h->hign_bytes, static_cast<size_t>(nq) * sizeof(int64_t)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->hign, ignore_ids, static_cast<size_t>(nq) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    ign_dev = h->hign;
+  }
+  rc = mips_search_local(h, h->hq, nq, k, q_normalize, ign_dev, 0, MIPS_ALGO_AUTO, h->hkey, h->hids,
+                         h->hxn2, h->hqn2, st);
+  if (rc) return rc;
+  rc = mips_merge(h->hkey, h->hids, h->hxn2, 1, nq, k, k, h->metric, out_mode, h->phi, h->hqn2, nullptr,
+                  h->hD, h->hI, nullptr, nullptr, 1.f, 0.f, nullptr, 0, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(D, h->hD, nk * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(I, h->hI, nk * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+"""B200FlatIndex — faiss-style flat exact index whose bank lives in HBM and whose search runs as
+hand-written sm_100a kernels behind the C ABI of include/mips_b200.h.
+
+It mirrors the part of the faiss `Index` protocol the reference consumes through HF `datasets`
+(sotasum/mips.py:333-345 add_faiss_index / .nprobe, :383-386 faiss_index.search;
+retriever_lightning.py:317-321, :400-404; pretrain.py:475-479, :519-523):
+`d`, `ntotal`, `metric_type`, `is_trained`, `verbose`, `train`, `add`, `search`, `reset`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, DTYPE_BF16, DTYPE_F32, MAX_K, OUT_AUGL2, OUT_IP,
+                   OUT_L2, check)
+
+METRIC_INNER_PRODUCT = 0  # faiss.METRIC_INNER_PRODUCT
+METRIC_L2 = 1  # faiss.METRIC_L2
+
+_DTYPES = {"fp32": DTYPE_F32, "float32": DTYPE_F32, "f32": DTYPE_F32, torch.float32: DTYPE_F32,
+           "bf16": DTYPE_BF16, "bfloat16": DTYPE_BF16, torch.bfloat16: DTYPE_BF16}
+_ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC}
+
+
+def _device_index(device) -> int:
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200FlatIndex needs a CUDA device (sm_100a); there is no CPU path")
+        return torch.cuda.current_device()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError(f"B200FlatIndex lives on a CUDA device, got {dev}")
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class B200FlatIndex:
+    """Exact flat index (inner product or L2) over a bf16 or fp32 bank resident in HBM."""
+
+    is_trained = True
+
+    def __init__(self, d: int, metric_type: int = METRIC_INNER_PRODUCT, dtype="bf16", device=None,
+                 capacity: int = 0, id_offset: int = 0):
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of 'bf16', 'fp32', got {dtype!r}")
+        self._L = _lib.lib()
+        self.device_index = _device_index(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._h = C.c_void_p()
+        check(self._L.mips_create(C.byref(self._h), int(d), int(metric_type), _DTYPES[dtype],
+                                  self.device_index, int(capacity)))
+        self.d = int(d)
+        self.metric_type = int(metric_type)
+        self.dtype = "bf16" if _DTYPES[dtype] == DTYPE_BF16 else "fp32"
+        self.id_offset = int(id_offset)  # global id of local row 0 (row-sharded banks)
+        self.verbose = False
+        self.nprobe = 1  # accepted and ignored: exact search (reference sets it at mips.py:342-345)
+
+    # ------------------------------------------------------------------ lifecycle
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._L.mips_destroy(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p()
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._L.mips_ntotal(self._h))
+
+    def reset(self) -> None:
+        check(self._L.mips_reset(self._h))
+
+    def train(self, x=None) -> None:  # flat index: nothing to train (datasets calls it when train_size is set)
+        return None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ build side
+    def add(self, x, normalize: bool = False) -> None:
+        """faiss Index.add: x float32 [n, d], numpy (host) or torch tensor (host or this device).
+        normalize=True fuses Mips._map_normalize (mips.py:358-361) into the ingest."""
+        if isinstance(x, torch.Tensor):
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise ValueError(f"Shape of vectors must be [n, {self.d}], got {tuple(x.shape)}")
+            if x.is_cuda:
+                if x.device != self.device:
+                    raise ValueError(f"vectors on {x.device}, index on {self.device}")
+                xc = x.detach().to(torch.float32).contiguous()
+                with torch.cuda.device(self.device):
+                    check(self._L.mips_add(self._h, _ptr(xc), xc.shape[0], 1, int(normalize), self._stream()))
+                    # xc must outlive the enqueued kernel
+                    xc.record_stream(torch.cuda.current_stream(self.device))
+                return
+            x = x.detach().to(torch.float32).contiguous().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"Shape of vectors must be [n, {self.d}], got {x.shape}")
+        with torch.cuda.device(self.device):
+            check(self._L.mips_add(self._h, x.ctypes.data_as(C.c_void_p), x.shape[0], 0, int(normalize),
+                                   self._stream()))
+
+    def max_norm2(self) -> float:
+        """max_i |x_i|^2 of the rows as added = get_phi (mips.py:55-56) = max_norm**2 (:298-304)."""
+        out = C.c_float()
+        check(self._L.mips_max_norm2(self._h, C.byref(out), self._stream()))
+        return float(out.value)
+
+    @property
+    def phi(self) -> float:
+        return float(self._L.mips_get_phi(self._h))
+
+    @phi.setter
+    def phi(self, v: float) -> None:
+        check(self._L.mips_set_phi(self._h, float(v)))
+
+    def reconstruct_n(self, i0: int = 0, n: Optional[int] = None, as_torch: bool = False):
+        """Stored rows [i0, i0+n) as float32 (bf16 banks return the rounded values)."""
+        n = self.ntotal - i0 if n is None else n
+        if as_torch:
+            out = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+            check(self._L.mips_reconstruct(self._h, i0, n, _ptr(out), 1, self._stream()))
+            return out
+        out = np.empty((n, self.d), dtype=np.float32)
+        check(self._L.mips_reconstruct(self._h, i0, n, out.ctypes.data_as(C.c_void_p), 0, self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ search side
+    def _check_k(self, k: int) -> int:
+        k = int(k)
+        if k < 1 or k > MAX_K:
+            raise ValueError(f"k must be in [1, {MAX_K}], got {k}")
+        return k
+
+    def search(self, xq, k: int, return_torch: bool = False):
+        """faiss Index.search(xq, k) -> (D float32 [nq,k], I int64 [nq,k]); IP scores descending,
+        L2 squared distances ascending, -1 padding. numpy in -> numpy out through the host entry
+        point (H2D + kernels + D2H in one C call); CUDA tensor in (or return_torch=True) keeps
+        everything on the device (removes the round trip of retriever_generator.py:143)."""
+        k = self._check_k(k)
+        if isinstance(xq, torch.Tensor) and (xq.is_cuda or return_torch):
+            r = self.search_ex(xq, k)
+            return r["scores"], r["ids"]
+        if isinstance(xq, torch.Tensor):
+            xq = xq.detach().cpu().numpy()
+        xq = np.asarray(xq)
+        if xq.ndim != 2:
+            raise ValueError("Shape of query must be 2D")
+        if xq.shape[1] != self.d:
+            raise ValueError(f"Query vectors must have dimension {self.d}, got {xq.shape[1]}")
+        xq = np.ascontiguousarray(xq, dtype=np.float32)
+        nq = xq.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        out_mode = OUT_IP if self.metric_type == METRIC_INNER_PRODUCT else OUT_L2
+        with torch.cuda.device(self.device):
+            check(self._L.mips_search_host(self._h, xq.ctypes.data_as(C.c_void_p), nq, k, 0, None, out_mode,
+                                           D.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p),
+                                           self._stream()))
+        if self.id_offset:
+            I = np.where(I >= 0, I + self.id_offset, I)
+        return D, I
+
+    def search_host(self, xq: np.ndarray, k: int, ignore_ids: Optional[np.ndarray] = None,
+                    normalize_queries: bool = False, out_mode: Optional[int] = None,
+                    D: Optional[np.ndarray] = None, I: Optional[np.ndarray] = None):
+        """The reference-facing end-to-end call (host buffers in and out, one C-ABI call):
+        Mips.search semantics incl. the per-query ignored id (mips.py:382-400). ids are local
+        (id_offset is not applied). D / I may be preallocated (e.g. pinned) arrays."""
+        k = self._check_k(k)
+        xq = np.ascontiguousarray(xq, dtype=np.float32)
+        if xq.ndim != 2 or xq.shape[1] != self.d:
+            raise ValueError(f"Shape of query must be [nq, {self.d}], got {xq.shape}")
+        nq = xq.shape[0]
+        D = np.empty((nq, k), dtype=np.float32) if D is None else D
+        I = np.empty((nq, k), dtype=np.int64) if I is None else I
+        ign = None
+        if ignore_ids is not None:
+            ign_arr = np.ascontiguousarray(ignore_ids, dtype=np.int64)
+            if ign_arr.shape != (nq,):
+                raise ValueError("ignore_ids must have one id per query")
+            ign = ign_arr.ctypes.data_as(C.c_void_p)
+        if out_mode is None:
+            out_mode = OUT_IP if self.metric_type == METRIC_INNER_PRODUCT else OUT_L2
+        with torch.cuda.device(self.device):
+            check(self._L.mips_search_host(self._h, xq.ctypes.data_as(C.c_void_p), nq, k,
+                                           int(normalize_queries), ign, int(out_mode),
+                                           D.ctypes.data_as(C.c_void_p), I.ctypes.data_as(C.c_void_p),
+                                           self._stream()))
+        return D, I
+
+    def search_local(self, xq: torch.Tensor, k: int, ignore_ids: Optional[torch.Tensor] = None,
+                     normalize_queries: bool = False, algo: str = "auto"):
+        """K1 + local merge on this shard: returns device tensors
+        (key [nq,k] descending ranking key, ids [nq,k] GLOBAL int64, xnorm2 [nq,k], qnorm2 [nq])."""
+        k = self._check_k(k)
+        if not isinstance(xq, torch.Tensor):
+            xq = torch.as_tensor(np.ascontiguousarray(xq, dtype=np.float32))
+        if xq.dim() != 2:
+            raise ValueError("Shape of query must be 2D")
+        if xq.shape[1] != self.d:
+            raise ValueError(f"Query vectors must have dimension {self.d}, got {xq.shape[1]}")
+        xq = xq.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        nq = xq.shape[0]
+        key = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        xn2 = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        qn2 = torch.empty((nq,), dtype=torch.float32, device=self.device)
+        ign = None
+        if ignore_ids is not None:
+            ign = torch.as_tensor(ignore_ids).to(device=self.device, dtype=torch.int64).contiguous()
+            if ign.shape != (nq,):
+                raise ValueError("ignore_ids must have one id per query")
+        with torch.cuda.device(self.device):
+            check(self._L.mips_search_local(self._h, _ptr(xq), nq, k, int(normalize_queries), _ptr(ign),
+                                            self.id_offset, _ALGOS[algo], _ptr(key), _ptr(ids), _ptr(xn2),
+                                            _ptr(qn2), self._stream()))
+        return key, ids, xn2, qn2
+
+    def merge(self, key: torch.Tensor, ids: torch.Tensor, xn2: Optional[torch.Tensor], qn2: Optional[torch.Tensor],
+              k: int, want: Iterable[str] = ("scores", "ids"), out_mode: Optional[int] = None,
+              ignore_ids: Optional[torch.Tensor] = None, mem_len: Optional[int] = None,
+              beta: float = 1.0, beta_bias: float = 0.0) -> dict:
+        """K2 over candidate lists [n_parts, nq, k_in] (one part per shard after the all-gather, or a
+        single local list): final (D, I) + the doc-score outputs of retriever_generator.py:158-193."""
+        return merge_candidates(key, ids, xn2, qn2, k, self.metric_type, want=want, out_mode=out_mode,
+                                phi=self.phi, ignore_ids=ignore_ids, mem_len=mem_len, beta=beta,
+                                beta_bias=beta_bias)
+
+    def search_ex(self, xq, k: int, ignore_ids=None, want: Iterable[str] = ("scores", "ids"),
+                  L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
+                  beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> dict:
+        """Device-resident search with optional fused outputs. want ⊆ {"scores","ids","cosine",
+        "doc_prob","memory_bias"}; L = memory_seq_len for memory_bias."""
+        key, ids, xn2, qn2 = self.search_local(xq, k, ignore_ids=ignore_ids,
+                                               normalize_queries=normalize_queries, algo=algo)
+        return self.merge(key.unsqueeze(0), ids.unsqueeze(0), xn2.unsqueeze(0), qn2, k, want=want,
+                          out_mode=out_mode, mem_len=L, beta=beta, beta_bias=beta_bias)
+
+    # ------------------------------------------------------------------ profiling hooks (bench)
+    def set_profiling(self, on: bool) -> None:
+        check(self._L.mips_set_profiling(self._h, int(on)))
+
+    def k1_ms_total(self):
+        return float(self._L.mips_k1_ms_total(self._h)), int(self._L.mips_prof_count(self._h))
+
+    @property
+    def last_algo(self) -> str:
+        return self._L.mips_last_algo(self._h).decode()
+
+
+def merge_candidates(key: torch.Tensor, ids: torch.Tensor, xn2: Optional[torch.Tensor],
+                     qn2: Optional[torch.Tensor], k: int, metric_type: int,
+                     want: Iterable[str] = ("scores", "ids"), out_mode: Optional[int] = None,
+                     phi: float = 0.0, ignore_ids: Optional[torch.Tensor] = None,
+                     mem_len: Optional[int] = None, beta: float = 1.0, beta_bias: float = 0.0) -> dict:
+    L = _lib.lib()
+    want = set(want)
+    unknown = want - {"scores", "ids", "cosine", "doc_prob", "memory_bias"}
+    if unknown:
+        raise ValueError(f"unknown outputs requested: {sorted(unknown)}")
+    if key.dim() != 3 or key.shape != ids.shape:
+        raise ValueError("candidates must be [n_parts, nq, k_in]")
+    if not key.is_cuda:
+        raise RuntimeError("merge runs on the GPU; candidates must be CUDA tensors")
+    dev = key.device
+    n_parts, nq, k_in = key.shape
+    key = key.contiguous()
+    ids = ids.contiguous()
+    xn2 = None if xn2 is None else xn2.contiguous()
+    if out_mode is None:
+        out_mode = OUT_IP if metric_type == METRIC_INNER_PRODUCT else OUT_L2
+    D = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    I = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    cosine = torch.empty((nq, k), dtype=torch.float32, device=dev) if want & {"cosine", "memory_bias", "doc_prob"} else None
+    doc_prob = torch.empty((nq, k), dtype=torch.float32, device=dev) if "doc_prob" in want else None
+    mbias = None
+    if "memory_bias" in want:
+        if not mem_len or mem_len < 1:
+            raise ValueError("memory_bias needs L (memory_seq_len) >= 1")
+        mbias = torch.empty((nq, k * int(mem_len)), dtype=torch.float32, device=dev)
+    ign = None if ignore_ids is None else torch.as_tensor(ignore_ids).to(device=dev, dtype=torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(L.mips_merge(_ptr(key), _ptr(ids), _ptr(xn2), n_parts, nq, k_in, int(k), int(metric_type),
+                           int(out_mode), float(phi), _ptr(qn2), _ptr(ign), _ptr(D), _ptr(I), _ptr(cosine),
+                           _ptr(doc_prob), float(beta), float(beta_bias), _ptr(mbias), int(mem_len or 0), st))
+    out = {"scores": D, "ids": I}
+    if cosine is not None:
+        out["cosine"] = cosine
+    if doc_prob is not None:
+        out["doc_prob"] = doc_prob
+    if mbias is not None:
+        out["memory_bias"] = mbias
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# faiss-module-shaped helpers (what the reference imports from `faiss` for this path)
+def IndexFlatIP(d: int, **kw) -> B200FlatIndex:
+    return B200FlatIndex(d, METRIC_INNER_PRODUCT, **kw)
+
+
+def IndexFlatL2(d: int, **kw) -> B200FlatIndex:
+    return B200FlatIndex(d, METRIC_L2, **kw)
+
+
+def IndexFlat(d: int, metric: int = METRIC_L2, **kw) -> B200FlatIndex:
+    return B200FlatIndex(d, metric, **kw)
+
+
+def index_factory(d: int, description: str = "Flat", metric: int = METRIC_L2, **kw) -> B200FlatIndex:
+    """faiss.index_factory for the exact path only (mips_string_factory "Flat",
+    model_config.py:50). Approximate factories (IVF*, HNSW*, SQ8 ...; sotasum/config.yaml:94)
+    are out of scope and rejected loudly."""
+    if description.strip() != "Flat":
+        raise ValueError(f"only the exact 'Flat' factory is supported, got {description!r}")
+    return B200FlatIndex(d, metric, **kw)
+
+
+def normalize_L2(x) -> None:
+    """faiss.normalize_L2(x): in-place row normalisation (mips.py:521-525), run on the GPU."""
+    L = _lib.lib()
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2:
+            raise ValueError("normalize_L2 needs a contiguous float32 [n, d] tensor")
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        check(L.mips_normalize_l2(_ptr(x), x.shape[0], x.shape[1], 1, x.device.index, st))
+        return
+    if not isinstance(x, np.ndarray) or x.dtype != np.float32 or not x.flags.c_contiguous or x.ndim != 2:
+        raise ValueError("normalize_L2 needs a C-contiguous float32 [n, d] array")
+    dev = _device_index(None)
+    check(L.mips_normalize_l2(x.ctypes.data_as(C.c_void_p), x.shape[0], x.shape[1], 0, dev, None))
