@@ -64,14 +64,17 @@ class B200FlatIndex:
         self.nprobe = 1  # accepted and ignored: exact search (reference sets it at mips.py:342-345)
 
     # ------------------------------------------------------------------ lifecycle
-    def __del__(self):
+    def close(self) -> None:
         h = getattr(self, "_h", None)
         if h is not None and h.value:
-            try:
-                self._L.mips_destroy(h)
-            except Exception:
-                pass
-            self._h = C.c_void_p()
+            self._L.mips_destroy(h)
+            h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter teardown
+            pass
 
     @property
     def ntotal(self) -> int:
