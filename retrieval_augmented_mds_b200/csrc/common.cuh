@@ -9,8 +9,8 @@
 //   bank    [capacity, d_pad]  row-major, bf16 or fp32, d_pad = round_up(d, 64), columns
 //                              [d, d_pad) are zero so kernels never need a K tail.
 //   norm2   [capacity]         fp32 |x|^2 of the STORED (rounded / normalised) row.
-// capacity is a multiple of 64 rows so a 64-row TMA box never leaves the allocation.
-constexpr int kRowAlign = 64;
+// capacity is a multiple of 128 rows so a 128-row TMA box never leaves the allocation.
+constexpr int kRowAlign = 128;
 constexpr int kDimAlign = 64;
 
 __host__ __device__ inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }

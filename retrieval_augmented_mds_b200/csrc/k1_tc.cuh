@@ -6,20 +6,27 @@
 //   * 128 queries per CTA = the 128 TMEM lanes. The query tile is STATIONARY: it is written once
 //     into TMEM columns [128, 128 + d_pad/2) as packed bf16 pairs and used as the A operand
 //     (tcgen05.mma with A in TMEM), so the only streamed operand is the bank.
-//   * bank rows stream HBM/L2 -> shared memory by TMA (64 rows x 64 k boxes, 128-byte swizzle),
-//     4 boxes (one 256-wide k slab) per pipeline stage, NUM_STAGES-deep mbarrier ring.
-//   * scores for 64 bank rows accumulate in one of two 64-column fp32 TMEM accumulators
-//     (M=128, N=64, K=16 instructions); the MMA of tile t+1 overlaps the epilogue of tile t.
-//   * epilogue: thread <-> query. Each thread pulls its lane's 64 scores (tcgen05.ld 32x32b),
+//   * bank rows stream HBM/L2 -> shared memory by TMA (ACC_N rows x 64 k boxes, 128-byte
+//     swizzle), SKCH boxes per pipeline stage, mbarrier full/empty ring.
+//   * scores accumulate in fp32 in the 128 TMEM columns left beside the query tile. Two layouts
+//     are compiled (template ACC_N):
+//       ACC_N = 128: one 128-row accumulator. Each M128xN128xK16 MMA occupies the tensor pipe for
+//                    64 cycles, which covers the read-modify-write latency of the accumulator, so
+//                    the 48 dependent MMAs of a tile stream back to back; the epilogue drain is
+//                    exposed once per tile (3072 MMA cycles).
+//       ACC_N = 64 : two 64-row accumulators (MMA of tile t+1 overlaps the epilogue of tile t),
+//                    but a dependent chain of N=64 MMAs (32 cycles each) is paced by the accumulator
+//                    round trip (~55 cycles, measured: tensor pipe 58 % busy).
+//   * epilogue: thread <-> query. Each thread pulls its lane's ACC_N scores (tcgen05.ld 32x32b),
 //     releases the accumulator, takes one max over them and compares with its running k-th best;
-//     only when something beats it (rare after warm-up) does it walk the 64 values and insert
+//     only when something beats it (rare after warm-up) does it walk the values and insert
 //     into its sorted list in shared memory. The [nq, N] score matrix never reaches HBM.
 //
 // Grid = n_qtiles * n_splits CTAs (<= #SMs): CTA (qtile, split) scans bank tiles
 // [split*T/S, (split+1)*T/S) for query tile qtile; CTAs of one split run side by side so a bank
 // tile is fetched from HBM once and served from L2 to the other query tiles.
 //
-// Roofline: tensor bound, 2*128*64*d_pad flops per tile; HBM bytes = one pass over
+// Roofline: tensor bound, 2*128*ACC_N*d_pad flops per tile; HBM bytes = one pass over
 // the bank per batch of <= 128*n_qtiles queries.
 #pragma once
 #include "common.cuh"
@@ -27,32 +34,36 @@
 
 namespace tc {
 constexpr int BLOCK_M = 128;                          // queries per CTA (TMEM lanes)
-constexpr int ACC_N = 64;                             // bank rows per accumulator
+constexpr int ACC_COLS = 128;                         // TMEM columns available for accumulators
 constexpr int KCH = 64;                               // bf16 per 128-byte swizzle row
-constexpr int BOX_BYTES = ACC_N * KCH * 2;            // 8 KiB: one TMA box
-constexpr int STAGE_KCH = 4;                          // boxes (k chunks) per stage
-constexpr int STAGE_BYTES = STAGE_KCH * BOX_BYTES;    // 32 KiB
 constexpr int TMEM_COLS = 512;
-constexpr int Q_COL0 = 2 * ACC_N;                     // query tile starts after the accumulators
+constexpr int Q_COL0 = ACC_COLS;                      // query tile starts after the accumulators
 constexpr int MAX_DPAD = (TMEM_COLS - Q_COL0) * 2;    // 768
 constexpr int THREADS = 192;                          // 4 epilogue warps + TMA warp + MMA warp
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;                    // 227 KiB opt-in maximum
 
 // shared memory: [align pad 1024][stages][lists][barriers]
+__host__ __device__ constexpr int box_bytes(int acc_n) { return acc_n * KCH * 2; }
 __host__ __device__ inline int list_bytes(int k) { return BLOCK_M * k * 8; }
 __host__ __device__ inline int bar_bytes() { return (2 * MAX_STAGES + 6) * 8; }
-inline int pick_stages(int k) {
-  int s = (SMEM_LIMIT - 1024 - list_bytes(k) - bar_bytes()) / STAGE_BYTES;
+// boxes (k chunks of 64) per stage: ~48 KiB stages when that divides d_pad/64, else ~32 KiB
+inline int pick_skch(int d_pad, int acc_n) {
+  const int n_kch = d_pad / KCH;
+  if (acc_n == 128) return n_kch % 3 == 0 ? 3 : 2;
+  return n_kch % 6 == 0 ? 6 : 4;
+}
+inline int pick_stages(int k, int skch, int acc_n) {
+  int s = (SMEM_LIMIT - 1024 - list_bytes(k) - bar_bytes()) / (skch * box_bytes(acc_n));
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
-inline size_t smem_bytes(int k, int stages) {
-  return 1024 + static_cast<size_t>(stages) * STAGE_BYTES + list_bytes(k) + bar_bytes();
+inline size_t smem_bytes(int k, int stages, int skch, int acc_n) {
+  return 1024 + static_cast<size_t>(stages) * skch * box_bytes(acc_n) + list_bytes(k) + bar_bytes();
 }
 
 struct Params {
   const __nv_bfloat16* q;   // [n_qtiles*128, d_pad] prepared queries (zero padded)
-  const float* xnorm2;      // [ntotal] (L2 only)
+  const float* xnorm2;      // [capacity] (L2 only)
   const int* ignore_local;  // [nq] or null
   float* part_key;          // [n_splits, nq, k]
   int* part_ids;
@@ -61,9 +72,16 @@ struct Params {
   unsigned long long cache_hint;
 };
 
-template <bool kL2>
+template <bool kL2, int ACC_N, int SKCH>
 __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
     const __grid_constant__ CUtensorMap tmap, const Params p) {
+  static_assert(ACC_N == 64 || ACC_N == 128, "accumulator width");
+  constexpr int NACC = ACC_COLS / ACC_N;                // 2 (double buffered) or 1
+  constexpr int BOX_BYTES = box_bytes(ACC_N);
+  constexpr int STAGE_KCH = SKCH;
+  constexpr int STAGE_BYTES = SKCH * BOX_BYTES;
+  constexpr int NGRP = ACC_N / 32;                      // tcgen05.ld.x32 groups per tile
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;   // 128B swizzle atoms need 1024B alignment
@@ -97,8 +115,8 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
       ptx::mbar_init(empty_bar(i), 1);   // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(tfull_bar(a), 1);          // tcgen05.commit
-      ptx::mbar_init(tempty_bar(a), BLOCK_M);   // every epilogue thread
+      ptx::mbar_init(tfull_bar(a), 1);    // tcgen05.commit
+      ptx::mbar_init(tempty_bar(a), 4);   // one elected lane per epilogue warp
     }
     ptx::mbar_init(qready_bar, BLOCK_M);
     ptx::fence_mbar_init();
@@ -111,6 +129,10 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+
+  // accumulator a of iteration `it`: buffer index and the parity of its full/empty barriers
+  auto acc_of = [](int it) { return NACC == 2 ? (it & 1) : 0; };
+  auto acc_par = [](int it) { return static_cast<uint32_t>(NACC == 2 ? ((it >> 1) & 1) : (it & 1)); };
 
   // The producer and MMA warps run their loops with all 32 lanes converged and elect one lane only
   // around the asynchronous instructions: descriptors and addresses then live in uniform
@@ -143,21 +165,34 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
+    // The barrier of the NEXT stage (and of the next tile's accumulator when it is double
+    // buffered) is probed with a non-blocking try_wait BEFORE this stage's MMAs are issued; its
+    // latency overlaps the issue and the blocking wait is only entered when the data is late.
     constexpr uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, ACC_N);
     ptx::mbar_wait(qready_bar, 0);
-    ptx::tc_fence_after();
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (tile0 < tile1) {
+      ptx::mbar_wait(full_bar(0), 0);
+      ptx::mbar_wait(tempty_bar(0), 1u);
+    }
+    ptx::tc_fence_after();
     for (int tile = tile0; tile < tile1; ++tile, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      ptx::tc_fence_after();
+      const int acc = acc_of(it);
       const uint32_t d_tmem = tmem_base + acc * ACC_N;
+      const bool last_tile = tile + 1 == tile1;
       for (int ks = 0; ks < n_kstages; ++ks) {
-        ptx::mbar_wait(full_bar(stage), phase);
-        ptx::tc_fence_after();
+        const bool last_ks = ks + 1 == n_kstages;
+        const int nstage = (stage + 1 == S) ? 0 : stage + 1;
+        const uint32_t nphase = (stage + 1 == S) ? phase ^ 1u : phase;
+        const bool has_next = !(last_tile && last_ks);
+        const bool next_ready = has_next ? ptx::mbar_try_wait(full_bar(nstage), nphase) : true;
+        const int nacc = acc_of(it + 1);
+        const uint32_t nacc_par = acc_par(it + 1) ^ 1u;
+        const bool probe_acc = NACC == 2 && last_ks && !last_tile;
+        const bool acc_ready = probe_acc ? ptx::mbar_try_wait(tempty_bar(nacc), nacc_par) : !(last_ks && !last_tile);
+
         const int nk = min(STAGE_KCH, n_kch - ks * STAGE_KCH);
         const uint32_t sbase = base + static_cast<uint32_t>(stage) * STAGE_BYTES;
         const uint32_t a_tmem0 = tmem_base + Q_COL0 + ks * (STAGE_KCH * KCH / 2);
@@ -175,14 +210,15 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
               }
             }
           }
-          ptx::mma_commit(empty_bar(stage));   // frees the stage once these MMAs have read it
-          if (ks == n_kstages - 1) ptx::mma_commit(tfull_bar(acc));   // accumulator complete
+          ptx::mma_commit(empty_bar(stage));              // frees the stage once these MMAs have read it
+          if (last_ks) ptx::mma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        if (!next_ready) ptx::mbar_wait(full_bar(nstage), nphase);
+        if (!acc_ready) ptx::mbar_wait(tempty_bar(nacc), nacc_par);
+        ptx::tc_fence_after();
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else {
@@ -216,58 +252,49 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
 
     int it = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      const int acc = acc_of(it);
+      ptx::mbar_wait(tfull_bar(acc), acc_par(it));
       __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent insert path
       ptx::tc_fence_after();
-      uint32_t v0[32], v1[32];
-      ptx::tmem_ld_x32(lane_addr + acc * ACC_N, v0);
-      ptx::tmem_ld_x32(lane_addr + acc * ACC_N + 32, v1);
+      uint32_t v[NGRP][32];
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) ptx::tmem_ld_x32(lane_addr + acc * ACC_N + g * 32, v[g]);
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty_bar(acc));   // accumulator is in registers: MMA may reuse it
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // accumulator is in registers: MMA may reuse it
 
       const int id0 = tile * ACC_N;
       if (kL2) {
         // ranking key for L2: <q,x> - |x|^2/2 (same for every lane: broadcast loads)
         const float4* xn = reinterpret_cast<const float4*>(p.xnorm2 + id0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(xn + j);
-          v0[4 * j + 0] = __float_as_uint(__uint_as_float(v0[4 * j + 0]) - 0.5f * t.x);
-          v0[4 * j + 1] = __float_as_uint(__uint_as_float(v0[4 * j + 1]) - 0.5f * t.y);
-          v0[4 * j + 2] = __float_as_uint(__uint_as_float(v0[4 * j + 2]) - 0.5f * t.z);
-          v0[4 * j + 3] = __float_as_uint(__uint_as_float(v0[4 * j + 3]) - 0.5f * t.w);
-        }
+        for (int g = 0; g < NGRP; ++g) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(xn + 8 + j);
-          v1[4 * j + 0] = __float_as_uint(__uint_as_float(v1[4 * j + 0]) - 0.5f * t.x);
-          v1[4 * j + 1] = __float_as_uint(__uint_as_float(v1[4 * j + 1]) - 0.5f * t.y);
-          v1[4 * j + 2] = __float_as_uint(__uint_as_float(v1[4 * j + 2]) - 0.5f * t.z);
-          v1[4 * j + 3] = __float_as_uint(__uint_as_float(v1[4 * j + 3]) - 0.5f * t.w);
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(xn + g * 8 + j);
+            v[g][4 * j + 0] = __float_as_uint(__uint_as_float(v[g][4 * j + 0]) - 0.5f * t.x);
+            v[g][4 * j + 1] = __float_as_uint(__uint_as_float(v[g][4 * j + 1]) - 0.5f * t.y);
+            v[g][4 * j + 2] = __float_as_uint(__uint_as_float(v[g][4 * j + 2]) - 0.5f * t.z);
+            v[g][4 * j + 3] = __float_as_uint(__uint_as_float(v[g][4 * j + 3]) - 0.5f * t.w);
+          }
         }
       }
       float m = -CUDART_INF_F;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        m = fmaxf(m, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+      for (int g = 0; g < NGRP; ++g)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[g][j]));
       if (m > thr && live) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v0[j]);
-          if (s > thr) {
-            const int id = id0 + j;
-            if (id < p.ntotal && id != ign) thr = topk_list_insert(lk, li, p.k, s, id);
-          }
-        }
+        for (int g = 0; g < NGRP; ++g) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v1[j]);
-          if (s > thr) {
-            const int id = id0 + 32 + j;
-            if (id < p.ntotal && id != ign) thr = topk_list_insert(lk, li, p.k, s, id);
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(v[g][j]);
+            if (s > thr) {
+              const int id = id0 + g * 32 + j;
+              if (id < p.ntotal && id != ign) thr = topk_list_insert(lk, li, p.k, s, id);
+            }
           }
         }
       }

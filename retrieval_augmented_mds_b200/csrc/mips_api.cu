@@ -58,7 +58,8 @@ struct mips_index_s {
   float phi = 0.f;
   int sm_count = 148;
   // TMA descriptor of the bank (re-encoded when the allocation changes)
-  CUtensorMap tmap;
+  CUtensorMap tmap128;   // 128-row boxes (single 128-wide accumulator kernel)
+  CUtensorMap tmap64;    // 64-row boxes (double-buffered 64-wide accumulator kernel)
   bool tmap_valid = false;
   // scratch (grown on demand; stable after warm-up)
   void* q_prep = nullptr;      size_t q_prep_bytes = 0;
@@ -123,12 +124,14 @@ static int encode_bank_tmap(mips_index_s* h) {
   if (!fn) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->d_pad), static_cast<cuuint64_t>(h->capacity)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(h->d_pad) * 2};
-  const cuuint32_t box[2] = {tc::KCH, tc::ACC_N};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(&h->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->bank, gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  for (int rows : {128, 64}) {
+    const cuuint32_t box[2] = {tc::KCH, static_cast<cuuint32_t>(rows)};
+    CUresult r = fn(rows == 128 ? &h->tmap128 : &h->tmap64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->bank,
+                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  }
   h->tmap_valid = true;
   return 0;
 }
@@ -177,10 +180,12 @@ static int set_kernel_attrs(mips_index_s* h) {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, simt_max));
   CUDA_TRY(cudaFuncSetAttribute(simt::search_simt_kernel<__nv_bfloat16, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, simt_max));
-  CUDA_TRY(cudaFuncSetAttribute(tc::search_tc_kernel<false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
-  CUDA_TRY(cudaFuncSetAttribute(tc::search_tc_kernel<true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+#define TC_ATTR(L2, N, K)                                                                      \
+  CUDA_TRY(cudaFuncSetAttribute(tc::search_tc_kernel<L2, N, K>,                                \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT))
+  TC_ATTR(false, 128, 3); TC_ATTR(true, 128, 3); TC_ATTR(false, 128, 2); TC_ATTR(true, 128, 2);
+  TC_ATTR(false, 64, 6);  TC_ATTR(true, 64, 6);  TC_ATTR(false, 64, 4);  TC_ATTR(true, 64, 4);
+#undef TC_ATTR
   h->attrs_set = true;
   return 0;
 }
@@ -456,13 +461,14 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
   }
 
   const bool l2 = h->metric == MIPS_METRIC_L2;
-  const bool use_tc = algo == MIPS_ALGO_TC;
+  const bool use_tc = algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC64;
   int n_parts = 0;
   const int slot = h->prof_n % kProfSlots;
   if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
 
   if (use_tc) {
-    const int n_tiles = static_cast<int>((h->ntotal + tc::ACC_N - 1) / tc::ACC_N);
+    const int acc_n = algo == MIPS_ALGO_TC64 ? 64 : 128;
+    const int n_tiles = static_cast<int>((h->ntotal + acc_n - 1) / acc_n);
     const int n_qtiles = nq_pad / tc::BLOCK_M;
     int n_splits = std::max(1, std::min(h->sm_count / n_qtiles, n_tiles));
     n_parts = n_splits;
@@ -484,17 +490,25 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     p.n_tiles = n_tiles;
     p.n_qtiles = n_qtiles;
     p.n_splits = n_splits;
-    p.stages = tc::pick_stages(k);
+    const int skch = tc::pick_skch(h->d_pad, acc_n);
+    p.stages = tc::pick_stages(k, skch, acc_n);
     // a bank tile is re-read by the other query tiles from L2; with one query tile it is dead
     p.cache_hint = n_qtiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
-    const size_t smem = tc::smem_bytes(k, p.stages);
+    const size_t smem = tc::smem_bytes(k, p.stages, skch, acc_n);
     const unsigned grid = static_cast<unsigned>(n_qtiles * n_splits);
-    if (l2)
-      tc::search_tc_kernel<true><<<grid, tc::THREADS, smem, st>>>(h->tmap, p);
-    else
-      tc::search_tc_kernel<false><<<grid, tc::THREADS, smem, st>>>(h->tmap, p);
+#define TC_LAUNCH(N, K, MAP)                                                               \
+  do {                                                                                     \
+    if (l2) tc::search_tc_kernel<true, N, K><<<grid, tc::THREADS, smem, st>>>(MAP, p);     \
+    else    tc::search_tc_kernel<false, N, K><<<grid, tc::THREADS, smem, st>>>(MAP, p);    \
+  } while (0)
+    if (acc_n == 128) {
+      if (skch == 3) TC_LAUNCH(128, 3, h->tmap128); else TC_LAUNCH(128, 2, h->tmap128);
+    } else {
+      if (skch == 6) TC_LAUNCH(64, 6, h->tmap64); else TC_LAUNCH(64, 4, h->tmap64);
+    }
+#undef TC_LAUNCH
     LAUNCH_CHECK("search_tc_kernel");
-    h->last_algo = "tc";
+    h->last_algo = acc_n == 128 ? "tc" : "tc64";
   } else {
     const int n_tiles = static_cast<int>((h->ntotal + simt::BN - 1) / simt::BN);
     const int n_qtiles = (nq + simt::BM - 1) / simt::BM;
@@ -547,9 +561,10 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tc_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc::MAX_DPAD && h->tmap_valid;
   if (algo == MIPS_ALGO_AUTO) algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
-  if (algo == MIPS_ALGO_TC && !tc_ok)
+  if ((algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC64) && !tc_ok)
     return set_err(MIPS_E_UNSUPPORTED, "tensor-core search needs a bf16 bank with d_pad <= %d", tc::MAX_DPAD);
-  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_SIMT) return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
+  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC64 && algo != MIPS_ALGO_SIMT)
+    return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
   if (h->ntotal == 0) {
     // faiss semantics on an empty index: ids -1
     CUDA_TRY(cudaMemsetAsync(out_ids, 0xff, static_cast<size_t>(nq) * k * sizeof(int64_t), st));
@@ -561,7 +576,7 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
     return 0;
   }
   // bound the scratch: chunks of queries (one kernel launch each)
-  const int chunk = algo == MIPS_ALGO_TC ? h->sm_count * tc::BLOCK_M : 16384;
+  const int chunk = algo != MIPS_ALGO_SIMT ? h->sm_count * tc::BLOCK_M : 16384;
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     const int m = std::min(chunk, nq - q0);
     int rc = search_chunk(h, q + static_cast<size_t>(q0) * h->d, m, k, q_normalize,

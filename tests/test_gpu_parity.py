@@ -84,10 +84,11 @@ def test_fp32_search_is_exact(m, metric, n, d, nq, k):
     assert np.array_equal(I, r["ids"]) and np.array_equal(D, r["scores"])
 
 
-@pytest.mark.parametrize("algo", ["tc", "simt"])
+@pytest.mark.parametrize("algo", ["tc", "tc64", "simt"])
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("n,d,nq,k", [(5000, 96, 37, 8), (20000, 768, 256, 8), (3001, 64, 1, 1),
-                                      (777, 256, 130, 33), (4096, 128, 64, 64), (64 * 300 + 5, 768, 300, 5)])
+                                      (777, 256, 130, 33), (4096, 128, 64, 64), (64 * 300 + 5, 768, 300, 5),
+                                      (10000, 320, 129, 16)])
 def test_bf16_search_matches_fp32_on_same_inputs(m, algo, metric, n, d, nq, k):
     xb, xq = _data(n, d, nq, seed=n + k + 1)
     idx = m.B200FlatIndex(d, metric, dtype="bf16")
