@@ -40,8 +40,9 @@ typedef struct mips_index_s* mips_handle;
 /* Search kernel selection (testing / bisection; AUTO is what the product uses). */
 #define MIPS_ALGO_AUTO 0
 #define MIPS_ALGO_SIMT 1   /* fp32 FMA tiled kernel, any dtype                     */
-#define MIPS_ALGO_TC 2     /* tcgen05/TMEM/TMA kernel, bf16 bank, d_pad <= 768     */
-#define MIPS_ALGO_TC64 3   /* same, 2 x 64-row double-buffered accumulators (A/B)  */
+#define MIPS_ALGO_TC 2     /* tcgen05/TMEM/TMA kernel, bf16 bank, d_pad <= 768:
+                              2 x 64-row double-buffered TMEM accumulators (default) */
+#define MIPS_ALGO_TC128 3  /* same kernel, one 128-row accumulator (A/B comparison) */
 
 /* Output transform applied by the merge kernel to the ranking key. */
 #define MIPS_OUT_IP 0      /* D = <q,x>                    descending (IndexFlatIP)          */

@@ -461,13 +461,13 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
   }
 
   const bool l2 = h->metric == MIPS_METRIC_L2;
-  const bool use_tc = algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC64;
+  const bool use_tc = algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128;
   int n_parts = 0;
   const int slot = h->prof_n % kProfSlots;
   if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
 
   if (use_tc) {
-    const int acc_n = algo == MIPS_ALGO_TC64 ? 64 : 128;
+    const int acc_n = algo == MIPS_ALGO_TC128 ? 128 : 64;
     const int n_tiles = static_cast<int>((h->ntotal + acc_n - 1) / acc_n);
     const int n_qtiles = nq_pad / tc::BLOCK_M;
     int n_splits = std::max(1, std::min(h->sm_count / n_qtiles, n_tiles));
@@ -508,7 +508,7 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     }
 #undef TC_LAUNCH
     LAUNCH_CHECK("search_tc_kernel");
-    h->last_algo = acc_n == 128 ? "tc" : "tc64";
+    h->last_algo = acc_n == 128 ? "tc128" : "tc";
   } else {
     const int n_tiles = static_cast<int>((h->ntotal + simt::BN - 1) / simt::BN);
     const int n_qtiles = (nq + simt::BM - 1) / simt::BM;
@@ -561,9 +561,9 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tc_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc::MAX_DPAD && h->tmap_valid;
   if (algo == MIPS_ALGO_AUTO) algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
-  if ((algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC64) && !tc_ok)
+  if ((algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128) && !tc_ok)
     return set_err(MIPS_E_UNSUPPORTED, "tensor-core search needs a bf16 bank with d_pad <= %d", tc::MAX_DPAD);
-  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC64 && algo != MIPS_ALGO_SIMT)
+  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC128 && algo != MIPS_ALGO_SIMT)
     return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
   if (h->ntotal == 0) {
     // faiss semantics on an empty index: ids -1

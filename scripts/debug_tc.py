@@ -48,7 +48,7 @@ def full_tile(d, n=64, nq=128, seed=0, algo="tc"):
 
 
 ok = True
-for algo in ("tc", "tc64"):
+for algo in ("tc", "tc128"):
     for d in (64, 128, 256, 320, 768):
         ok &= full_tile(d, algo=algo)
     ok &= full_tile(768, n=128, algo=algo)
@@ -61,7 +61,7 @@ for n in (128, 640, 6400 + 17):
     idx = m.B200FlatIndex(d, 0, dtype="bf16")
     idx.add(xb)
     b = idx.search_ex(torch.from_numpy(xq), k, algo="simt")
-    for algo in ("tc", "tc64"):
+    for algo in ("tc", "tc128"):
         a = idx.search_ex(torch.from_numpy(xq), k, algo=algo)
         torch.cuda.synchronize()
         same = (a["ids"] == b["ids"]).float().mean().item()

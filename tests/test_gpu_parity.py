@@ -84,7 +84,7 @@ def test_fp32_search_is_exact(m, metric, n, d, nq, k):
     assert np.array_equal(I, r["ids"]) and np.array_equal(D, r["scores"])
 
 
-@pytest.mark.parametrize("algo", ["tc", "tc64", "simt"])
+@pytest.mark.parametrize("algo", ["tc", "tc128", "simt"])
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("n,d,nq,k", [(5000, 96, 37, 8), (20000, 768, 256, 8), (3001, 64, 1, 1),
                                       (777, 256, 130, 33), (4096, 128, 64, 64), (64 * 300 + 5, 768, 300, 5),
