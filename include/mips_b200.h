@@ -130,6 +130,18 @@ int mips_merge(const float* cand_key, const int64_t* cand_ids, const float* cand
                float* D, int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias,
                float* memory_bias, int mem_len, void* stream);
 
+/* Packed variants for the multi-GPU path: candidates travel as 16-byte records
+ * {float key; float xnorm2; int64 id} so that ONE all-gather moves a rank's [nq, k] list and no
+ * pack/unpack kernels are needed around it (ncclAllGather of per-rank top-k, then K2).
+ *   out_packed   device [nq, k] records            cand_packed  device [n_parts, nq, k_in] records */
+int mips_search_local_packed(mips_handle h, const float* q, int nq, int k, int q_normalize,
+                             const int64_t* ignore_ids, int64_t id_offset, int algo, void* out_packed,
+                             float* out_qnorm2, void* stream);
+int mips_merge_packed(const void* cand_packed, int n_parts, int nq, int k_in, int k_out, int metric,
+                      int out_mode, float phi, const float* q_norm2, const int64_t* ignore_ids, float* D,
+                      int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias,
+                      float* memory_bias, int mem_len, void* stream);
+
 /* End-to-end host call: what `Mips.search` does today with numpy in / numpy out
  * (reference mips.py:382-400). H2D of queries, K1, K2, D2H of (D, I); sync.
  * xq host fp32 [nq, d]; ignore_ids host int64 [nq] or NULL; D host fp32 [nq,k]; I host int64 [nq,k]. */

@@ -56,6 +56,9 @@ def lib() -> C.CDLL:
         "mips_search_local": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp]),
         "mips_merge": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp,
                              f32, f32, vp, i32, vp]),
+        "mips_search_local_packed": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, vp]),
+        "mips_merge_packed": (i32, [vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, f32, f32,
+                                    vp, i32, vp]),
         "mips_search_host": (i32, [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]),
         "mips_last_error": (C.c_char_p, []),
         "mips_launch_count": (i64, []),

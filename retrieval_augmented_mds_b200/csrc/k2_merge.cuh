@@ -15,6 +15,13 @@
 #include "common.cuh"
 #include "mips_b200.h"
 
+// One candidate as it travels through the all-gather: 16 bytes.
+struct __align__(16) PackedCand {
+  float key;
+  float xn2;
+  int64_t id;
+};
+
 struct MergeBest {
   float key;
   int64_t id;
@@ -34,7 +41,9 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     const int64_t* __restrict__ ignore_ids, int metric, int out_mode, float phi,
     const float* __restrict__ q_norm2, float* __restrict__ out_key, int64_t* __restrict__ out_ids,
     float* __restrict__ out_xn2, float* __restrict__ cosine, float* __restrict__ doc_prob,
-    float beta, float beta_bias, float* __restrict__ memory_bias, int mem_len) {
+    float beta, float beta_bias, float* __restrict__ memory_bias, int mem_len,
+    const PackedCand* __restrict__ cand_packed,   // !LOCAL: packed input instead of the 3 arrays
+    PackedCand* __restrict__ out_packed) {        // LOCAL: packed output instead of the 3 arrays
   __shared__ float s_key[4][MIPS_MAX_K];
   __shared__ float s_xn2[4][MIPS_MAX_K];
   __shared__ float s_cos[4][MIPS_MAX_K];
@@ -56,14 +65,20 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
       const int p = c / k_in, s = c - p * k_in;
       const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + s;
       int64_t id;
+      float key;
       if (LOCAL) {
         const int32_t l = ids32[a];
         id = l < 0 ? -1 : id_offset + l;
+        key = cand_key[a];
+      } else if (cand_packed) {
+        const PackedCand pc = cand_packed[a];
+        id = pc.id;
+        key = pc.key;
       } else {
         id = ids64[a];
+        key = cand_key[a];
       }
       if (id < 0 || id == ign) continue;
-      const float key = cand_key[a];
       const bool after = (key < prev_key) || (key == prev_key && id > prev_id);
       if (!after) continue;
       if (merge_better(key, id, b.key, b.id)) {
@@ -92,11 +107,13 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
       if (LOCAL) {
         if (bank_xn2) xn = bank_xn2[b.id - id_offset];
       } else {
-        if (cand_xn2) xn = cand_xn2[b.pos];
+        if (cand_packed) xn = cand_packed[b.pos].xn2;
+        else if (cand_xn2) xn = cand_xn2[b.pos];
       }
       s_key[w][j] = b.key;
       s_xn2[w][j] = xn;
-      out_ids[static_cast<size_t>(q) * k_out + j] = b.id;
+      if (LOCAL && out_packed) out_packed[static_cast<size_t>(q) * k_out + j] = PackedCand{b.key, xn, b.id};
+      else out_ids[static_cast<size_t>(q) * k_out + j] = b.id;
     }
   }
   __syncwarp();
@@ -106,6 +123,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
   for (int j = lane; j < k_out; j += 32) {
     const size_t o = static_cast<size_t>(q) * k_out + j;
     if (j >= n_found) {
+      if (LOCAL && out_packed) {
+        out_packed[o] = PackedCand{-CUDART_INF_F, 0.f, -1};
+        continue;
+      }
       out_ids[o] = -1;
       if (LOCAL) {
         out_key[o] = -CUDART_INF_F;
@@ -119,8 +140,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     }
     const float key = s_key[w][j], xn = s_xn2[w][j];
     if (LOCAL) {
-      out_key[o] = key;
-      if (out_xn2) out_xn2[o] = xn;
+      if (!out_packed) {
+        out_key[o] = key;
+        if (out_xn2) out_xn2[o] = xn;
+      }
       continue;
     }
     // ranking key -> inner product

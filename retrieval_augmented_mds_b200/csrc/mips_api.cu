@@ -436,7 +436,8 @@ int mips_reconstruct(mips_handle h, int64_t row0, int64_t n, float* out, int out
 // ------------------------------------------------------------------------------------------ K1
 static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_normalize,
                         const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
-                        int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, cudaStream_t st) {
+                        int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
+                        cudaStream_t st) {
   int rc;
   const size_t eb = elem_bytes(h);
   const int nq_pad = round_up_i(nq, tc::BLOCK_M);
@@ -545,16 +546,19 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
   // local k-way merge: split lists -> one list per query, global ids, |x|^2 gathered
   merge_topk_kernel<true><<<(nq + 3) / 4, 128, 0, st>>>(
       h->part_key, h->part_ids, nullptr, h->norm2, n_parts, nq, k, k, id_offset, nullptr, h->metric,
-      MIPS_OUT_IP, 0.f, nullptr, out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0);
+      MIPS_OUT_IP, 0.f, nullptr, out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
+      static_cast<PackedCand*>(out_packed));
   LAUNCH_CHECK("merge_topk_kernel<local>");
   return 0;
 }
 
-int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normalize,
-                      const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
-                      int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* stream) {
+static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q_normalize,
+                             const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
+                             int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
+                             void* stream) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
-  if (nq < 0 || (nq > 0 && (!q || !out_key || !out_ids))) return set_err(MIPS_E_INVALID, "bad q / outputs");
+  if (nq < 0 || (nq > 0 && (!q || (!out_packed && (!out_key || !out_ids)))))
+    return set_err(MIPS_E_INVALID, "bad q / outputs");
   if (k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "k must be in [1, %d], got %d", MIPS_MAX_K, k);
   if (nq == 0) return 0;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -567,10 +571,10 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
     return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
   if (h->ntotal == 0) {
     // faiss semantics on an empty index: ids -1
-    CUDA_TRY(cudaMemsetAsync(out_ids, 0xff, static_cast<size_t>(nq) * k * sizeof(int64_t), st));
     merge_topk_kernel<true><<<(nq + 3) / 4, 128, 0, st>>>(
         nullptr, nullptr, nullptr, nullptr, 0, nq, k, k, 0, nullptr, h->metric, MIPS_OUT_IP, 0.f, nullptr,
-        out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0);
+        out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
+        static_cast<PackedCand*>(out_packed));
     LAUNCH_CHECK("merge_topk_kernel<empty>");
     if (out_qnorm2) CUDA_TRY(cudaMemsetAsync(out_qnorm2, 0, static_cast<size_t>(nq) * sizeof(float), st));
     return 0;
@@ -581,35 +585,73 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
     const int m = std::min(chunk, nq - q0);
     int rc = search_chunk(h, q + static_cast<size_t>(q0) * h->d, m, k, q_normalize,
                           ignore_ids ? ignore_ids + q0 : nullptr, id_offset, algo,
-                          out_key + static_cast<size_t>(q0) * k, out_ids + static_cast<size_t>(q0) * k,
+                          out_key ? out_key + static_cast<size_t>(q0) * k : nullptr,
+                          out_ids ? out_ids + static_cast<size_t>(q0) * k : nullptr,
                           out_xnorm2 ? out_xnorm2 + static_cast<size_t>(q0) * k : nullptr,
-                          out_qnorm2 ? out_qnorm2 + q0 : nullptr, st);
+                          out_qnorm2 ? out_qnorm2 + q0 : nullptr,
+                          out_packed ? static_cast<PackedCand*>(out_packed) + static_cast<size_t>(q0) * k : nullptr,
+                          st);
     if (rc) return rc;
   }
   return 0;
 }
 
+int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normalize,
+                      const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
+                      int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* stream) {
+  return search_local_impl(h, q, nq, k, q_normalize, ignore_ids, id_offset, algo, out_key, out_ids,
+                           out_xnorm2, out_qnorm2, nullptr, stream);
+}
+
+int mips_search_local_packed(mips_handle h, const float* q, int nq, int k, int q_normalize,
+                             const int64_t* ignore_ids, int64_t id_offset, int algo, void* out_packed,
+                             float* out_qnorm2, void* stream) {
+  if (!out_packed && nq > 0) return set_err(MIPS_E_INVALID, "out_packed is NULL");
+  return search_local_impl(h, q, nq, k, q_normalize, ignore_ids, id_offset, algo, nullptr, nullptr, nullptr,
+                           out_qnorm2, out_packed, stream);
+}
+
 // ------------------------------------------------------------------------------------------ K2
-int mips_merge(const float* cand_key, const int64_t* cand_ids, const float* cand_xnorm2, int n_parts,
+static int merge_impl(const float* cand_key, const int64_t* cand_ids, const float* cand_xnorm2,
+                      const void* cand_packed, int n_parts,
                int nq, int k_in, int k_out, int metric, int out_mode, float phi, const float* q_norm2,
                const int64_t* ignore_ids, float* D, int64_t* I, float* cosine, float* doc_prob,
                float beta, float beta_bias, float* memory_bias, int mem_len, void* stream) {
   if (nq < 0 || n_parts < 0 || k_in < 1 || k_out < 1 || k_out > MIPS_MAX_K)
     return set_err(MIPS_E_INVALID, "bad merge shape (n_parts=%d nq=%d k_in=%d k_out=%d)", n_parts, nq, k_in, k_out);
   if (nq == 0) return 0;
-  if (!D || !I || (n_parts > 0 && (!cand_key || !cand_ids))) return set_err(MIPS_E_INVALID, "null buffers");
+  if (!D || !I || (n_parts > 0 && !cand_packed && (!cand_key || !cand_ids)))
+    return set_err(MIPS_E_INVALID, "null buffers");
   if (out_mode < MIPS_OUT_IP || out_mode > MIPS_OUT_AUGL2) return set_err(MIPS_E_INVALID, "bad out_mode %d", out_mode);
   const bool need_xn2 = out_mode == MIPS_OUT_L2 || metric == MIPS_METRIC_L2 || cosine || doc_prob || memory_bias;
-  if (need_xn2 && n_parts > 0 && !cand_xnorm2) return set_err(MIPS_E_INVALID, "cand_xnorm2 required for L2 / cosine outputs");
+  if (need_xn2 && n_parts > 0 && !cand_xnorm2 && !cand_packed) return set_err(MIPS_E_INVALID, "cand_xnorm2 required for L2 / cosine outputs");
   if ((out_mode != MIPS_OUT_IP || cosine || doc_prob || memory_bias) && !q_norm2)
     return set_err(MIPS_E_INVALID, "q_norm2 required for L2 / cosine outputs");
   if (memory_bias && mem_len < 1) return set_err(MIPS_E_INVALID, "mem_len must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   merge_topk_kernel<false><<<(nq + 3) / 4, 128, 0, st>>>(
       cand_key, cand_ids, cand_xnorm2, nullptr, n_parts, nq, k_in, k_out, 0, ignore_ids, metric, out_mode,
-      phi, q_norm2, D, I, nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len);
+      phi, q_norm2, D, I, nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len,
+      static_cast<const PackedCand*>(cand_packed), nullptr);
   LAUNCH_CHECK("merge_topk_kernel<final>");
   return 0;
+}
+
+int mips_merge(const float* cand_key, const int64_t* cand_ids, const float* cand_xnorm2, int n_parts,
+               int nq, int k_in, int k_out, int metric, int out_mode, float phi, const float* q_norm2,
+               const int64_t* ignore_ids, float* D, int64_t* I, float* cosine, float* doc_prob,
+               float beta, float beta_bias, float* memory_bias, int mem_len, void* stream) {
+  return merge_impl(cand_key, cand_ids, cand_xnorm2, nullptr, n_parts, nq, k_in, k_out, metric, out_mode, phi,
+                    q_norm2, ignore_ids, D, I, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, stream);
+}
+
+int mips_merge_packed(const void* cand_packed, int n_parts, int nq, int k_in, int k_out, int metric,
+                      int out_mode, float phi, const float* q_norm2, const int64_t* ignore_ids, float* D,
+                      int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias,
+                      float* memory_bias, int mem_len, void* stream) {
+  if (!cand_packed && n_parts > 0 && nq > 0) return set_err(MIPS_E_INVALID, "cand_packed is NULL");
+  return merge_impl(nullptr, nullptr, nullptr, cand_packed, n_parts, nq, k_in, k_out, metric, out_mode, phi,
+                    q_norm2, ignore_ids, D, I, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, stream);
 }
 
 // ------------------------------------------------------------------------------------------ e2e

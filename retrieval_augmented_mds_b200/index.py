@@ -230,6 +230,32 @@ class B200FlatIndex:
                                             _ptr(qn2), self._stream()))
         return key, ids, xn2, qn2
 
+    def search_local_packed(self, xq: torch.Tensor, k: int, ignore_ids: Optional[torch.Tensor] = None,
+                            normalize_queries: bool = False, algo: str = "auto"):
+        """K1 + local merge with the result as 16-byte records {f32 key, f32 |x|^2, i64 global id}:
+        returns (packed uint8 [nq, k, 16], qnorm2 [nq]) — the buffer one all-gather moves."""
+        k = self._check_k(k)
+        if not isinstance(xq, torch.Tensor):
+            xq = torch.as_tensor(np.ascontiguousarray(xq, dtype=np.float32))
+        if xq.dim() != 2:
+            raise ValueError("Shape of query must be 2D")
+        if xq.shape[1] != self.d:
+            raise ValueError(f"Query vectors must have dimension {self.d}, got {xq.shape[1]}")
+        xq = xq.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        nq = xq.shape[0]
+        packed = torch.empty((nq, k, 16), dtype=torch.uint8, device=self.device)
+        qn2 = torch.empty((nq,), dtype=torch.float32, device=self.device)
+        ign = None
+        if ignore_ids is not None:
+            ign = torch.as_tensor(ignore_ids).to(device=self.device, dtype=torch.int64).contiguous()
+            if ign.shape != (nq,):
+                raise ValueError("ignore_ids must have one id per query")
+        with torch.cuda.device(self.device):
+            check(self._L.mips_search_local_packed(self._h, _ptr(xq), nq, k, int(normalize_queries), _ptr(ign),
+                                                   self.id_offset, _ALGOS[algo], _ptr(packed), _ptr(qn2),
+                                                   self._stream()))
+        return packed, qn2
+
     def merge(self, key: torch.Tensor, ids: torch.Tensor, xn2: Optional[torch.Tensor], qn2: Optional[torch.Tensor],
               k: int, want: Iterable[str] = ("scores", "ids"), out_mode: Optional[int] = None,
               ignore_ids: Optional[torch.Tensor] = None, mem_len: Optional[int] = None,
@@ -239,6 +265,12 @@ class B200FlatIndex:
         return merge_candidates(key, ids, xn2, qn2, k, self.metric_type, want=want, out_mode=out_mode,
                                 phi=self.phi, ignore_ids=ignore_ids, mem_len=mem_len, beta=beta,
                                 beta_bias=beta_bias)
+
+    def merge_packed(self, packed: torch.Tensor, qn2: Optional[torch.Tensor], k: int,
+                     want: Iterable[str] = ("scores", "ids"), out_mode: Optional[int] = None,
+                     mem_len: Optional[int] = None, beta: float = 1.0, beta_bias: float = 0.0) -> dict:
+        return merge_candidates(None, None, None, qn2, k, self.metric_type, want=want, out_mode=out_mode,
+                                phi=self.phi, mem_len=mem_len, beta=beta, beta_bias=beta_bias, packed=packed)
 
     def search_ex(self, xq, k: int, ignore_ids=None, want: Iterable[str] = ("scores", "ids"),
                   L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
@@ -262,25 +294,35 @@ class B200FlatIndex:
         return self._L.mips_last_algo(self._h).decode()
 
 
-def merge_candidates(key: torch.Tensor, ids: torch.Tensor, xn2: Optional[torch.Tensor],
+def merge_candidates(key: Optional[torch.Tensor], ids: Optional[torch.Tensor], xn2: Optional[torch.Tensor],
                      qn2: Optional[torch.Tensor], k: int, metric_type: int,
                      want: Iterable[str] = ("scores", "ids"), out_mode: Optional[int] = None,
                      phi: float = 0.0, ignore_ids: Optional[torch.Tensor] = None,
-                     mem_len: Optional[int] = None, beta: float = 1.0, beta_bias: float = 0.0) -> dict:
+                     mem_len: Optional[int] = None, beta: float = 1.0, beta_bias: float = 0.0,
+                     packed: Optional[torch.Tensor] = None) -> dict:
+    """K2. Candidates either as three arrays [n_parts, nq, k_in] (key, ids, xn2) or as one packed
+    uint8 tensor [n_parts, nq, k_in, 16] of {f32 key, f32 |x|^2, i64 id} records."""
     L = _lib.lib()
     want = set(want)
     unknown = want - {"scores", "ids", "cosine", "doc_prob", "memory_bias"}
     if unknown:
         raise ValueError(f"unknown outputs requested: {sorted(unknown)}")
-    if key.dim() != 3 or key.shape != ids.shape:
-        raise ValueError("candidates must be [n_parts, nq, k_in]")
-    if not key.is_cuda:
+    if packed is not None:
+        if packed.dim() != 4 or packed.shape[-1] != 16 or packed.dtype != torch.uint8:
+            raise ValueError("packed candidates must be uint8 [n_parts, nq, k_in, 16]")
+        src = packed = packed.contiguous()
+        n_parts, nq, k_in = packed.shape[:3]
+    else:
+        if key.dim() != 3 or key.shape != ids.shape:
+            raise ValueError("candidates must be [n_parts, nq, k_in]")
+        src = key
+        n_parts, nq, k_in = key.shape
+        key = key.contiguous()
+        ids = ids.contiguous()
+        xn2 = None if xn2 is None else xn2.contiguous()
+    if not src.is_cuda:
         raise RuntimeError("merge runs on the GPU; candidates must be CUDA tensors")
-    dev = key.device
-    n_parts, nq, k_in = key.shape
-    key = key.contiguous()
-    ids = ids.contiguous()
-    xn2 = None if xn2 is None else xn2.contiguous()
+    dev = src.device
     if out_mode is None:
         out_mode = OUT_IP if metric_type == METRIC_INNER_PRODUCT else OUT_L2
     D = torch.empty((nq, k), dtype=torch.float32, device=dev)
@@ -295,9 +337,15 @@ def merge_candidates(key: torch.Tensor, ids: torch.Tensor, xn2: Optional[torch.T
     ign = None if ignore_ids is None else torch.as_tensor(ignore_ids).to(device=dev, dtype=torch.int64).contiguous()
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        check(L.mips_merge(_ptr(key), _ptr(ids), _ptr(xn2), n_parts, nq, k_in, int(k), int(metric_type),
-                           int(out_mode), float(phi), _ptr(qn2), _ptr(ign), _ptr(D), _ptr(I), _ptr(cosine),
-                           _ptr(doc_prob), float(beta), float(beta_bias), _ptr(mbias), int(mem_len or 0), st))
+        if packed is not None:
+            check(L.mips_merge_packed(_ptr(packed), n_parts, nq, k_in, int(k), int(metric_type), int(out_mode),
+                                      float(phi), _ptr(qn2), _ptr(ign), _ptr(D), _ptr(I), _ptr(cosine),
+                                      _ptr(doc_prob), float(beta), float(beta_bias), _ptr(mbias),
+                                      int(mem_len or 0), st))
+        else:
+            check(L.mips_merge(_ptr(key), _ptr(ids), _ptr(xn2), n_parts, nq, k_in, int(k), int(metric_type),
+                               int(out_mode), float(phi), _ptr(qn2), _ptr(ign), _ptr(D), _ptr(I), _ptr(cosine),
+                               _ptr(doc_prob), float(beta), float(beta_bias), _ptr(mbias), int(mem_len or 0), st))
     out = {"scores": D, "ids": I}
     if cosine is not None:
         out["cosine"] = cosine

@@ -66,6 +66,16 @@ def gather_candidates(key: torch.Tensor, ids: torch.Tensor, xn2: torch.Tensor, g
     return g_key, g_ids, g_xn2
 
 
+def gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """THE exchange step of the search path: one all-gather of each rank's packed top-k list
+    (uint8 [nq, k, 16] -> [G, nq, k, 16]); 16*nq*k bytes per rank (128 KiB at nq=1024, k=8)."""
+    world = dist.get_world_size(group)
+    nq, k, rec = packed.shape
+    out = torch.empty((world * nq, k, rec), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    return out.view(world, nq, k, rec)
+
+
 class ShardedFlatIndex:
     """B200FlatIndex per rank + NCCL all-gather + K2 merge. Queries are replicated on all ranks
     (every rank passes the same xq) and every rank ends with the full result."""
@@ -105,11 +115,8 @@ class ShardedFlatIndex:
     def search(self, xq, k: int, ignore_ids=None, want: Iterable[str] = ("scores", "ids"),
                L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
                beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> dict:
-        key, ids, xn2, qn2 = self.local.search_local(xq, k, ignore_ids=ignore_ids,
+        packed, qn2 = self.local.search_local_packed(xq, k, ignore_ids=ignore_ids,
                                                      normalize_queries=normalize_queries, algo=algo)
-        if self.world > 1:
-            g_key, g_ids, g_xn2 = gather_candidates(key, ids, xn2, self.group)
-        else:
-            g_key, g_ids, g_xn2 = key.unsqueeze(0), ids.unsqueeze(0), xn2.unsqueeze(0)
-        return self.local.merge(g_key, g_ids, g_xn2, qn2, k, want=want, out_mode=out_mode, mem_len=L,
-                                beta=beta, beta_bias=beta_bias)
+        gathered = gather_packed(packed, self.group) if self.world > 1 else packed.unsqueeze(0)
+        return self.local.merge_packed(gathered, qn2, k, want=want, out_mode=out_mode, mem_len=L,
+                                       beta=beta, beta_bias=beta_bias)

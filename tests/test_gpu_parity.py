@@ -274,18 +274,23 @@ def test_sharded_merge_is_shard_count_invariant(m):
     one.add(xb)
     ref = _search_np(one, xq, 8, want=("scores", "ids", "cosine"))
     for G in (2, 3, 8):
-        keys, ids, xn2s, qn2 = [], [], [], None
+        keys, ids, xn2s, packs, qn2 = [], [], [], [], None
         for r in range(G):
             rows = balanced_range(len(xb), r, G)
             sh = m.B200FlatIndex(256, 0, dtype="bf16", id_offset=rows.start)
             sh.add(xb[rows.start:rows.stop])
             kk, ii, xx, qn2 = sh.search_local(torch.from_numpy(xq), 8)
             keys.append(kk), ids.append(ii), xn2s.append(xx)
+            pk, _ = sh.search_local_packed(torch.from_numpy(xq), 8)  # the record format the all-gather moves
+            packs.append(pk)
         out = m.merge_candidates(torch.stack(keys), torch.stack(ids), torch.stack(xn2s), qn2, 8, 0,
                                  want=("scores", "ids", "cosine"))
-        assert np.array_equal(out["ids"].cpu().numpy(), ref["ids"])
-        np.testing.assert_allclose(out["scores"].cpu().numpy(), ref["scores"], rtol=1e-6)
-        np.testing.assert_allclose(out["cosine"].cpu().numpy(), ref["cosine"], rtol=1e-6)
+        outp = m.merge_candidates(None, None, None, qn2, 8, 0, want=("scores", "ids", "cosine"),
+                                  packed=torch.stack(packs))
+        for o_ in (out, outp):
+            assert np.array_equal(o_["ids"].cpu().numpy(), ref["ids"])
+            np.testing.assert_allclose(o_["scores"].cpu().numpy(), ref["scores"], rtol=1e-6)
+            np.testing.assert_allclose(o_["cosine"].cpu().numpy(), ref["cosine"], rtol=1e-6)
 
 
 def test_growth_preserves_rows_and_results(m):

@@ -70,6 +70,15 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         assert g_key.shape == (world, nq, k) and g_ids.dtype == torch.int64
         assert torch.equal(g_key[rank], torch.from_numpy(D)) and torch.equal(g_ids[rank], torch.from_numpy(I + off))
         assert torch.equal(g_xn2[rank], torch.from_numpy(xn2))
+        # the packed exchange used by the product path: {f32 key, f32 |x|^2, i64 id} records
+        rec = np.zeros((nq, k), dtype=np.dtype([("key", "<f4"), ("xn2", "<f4"), ("id", "<i8")]))
+        rec["key"], rec["xn2"], rec["id"] = D, xn2, I + off
+        assert rec.dtype.itemsize == 16
+        packed = torch.from_numpy(rec.view(np.uint8).reshape(nq, k, 16).copy())
+        g_packed = sharded.gather_packed(packed)
+        assert g_packed.shape == (world, nq, k, 16)
+        back = g_packed.numpy().reshape(world, nq, k * 16).view(rec.dtype).reshape(world, nq, k)
+        assert np.array_equal(back["key"], g_key.numpy()) and np.array_equal(back["id"], g_ids.numpy())
         # merging the gathered lists (oracle ordering rule) reproduces the unsharded search
         cat_s = g_key.permute(1, 0, 2).reshape(nq, -1).numpy()
         cat_i = g_ids.permute(1, 0, 2).reshape(nq, -1).numpy()
