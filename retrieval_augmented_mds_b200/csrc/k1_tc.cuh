@@ -9,14 +9,16 @@
 //   * bank rows stream HBM/L2 -> shared memory by TMA (ACC_N rows x 64 k boxes, 128-byte
 //     swizzle), SKCH boxes per pipeline stage, mbarrier full/empty ring.
 //   * scores accumulate in fp32 in the 128 TMEM columns left beside the query tile. Two layouts
-//     are compiled (template ACC_N):
-//       ACC_N = 128: one 128-row accumulator. Each M128xN128xK16 MMA occupies the tensor pipe for
-//                    64 cycles, which covers the read-modify-write latency of the accumulator, so
-//                    the 48 dependent MMAs of a tile stream back to back; the epilogue drain is
-//                    exposed once per tile (3072 MMA cycles).
-//       ACC_N = 64 : two 64-row accumulators (MMA of tile t+1 overlaps the epilogue of tile t),
-//                    but a dependent chain of N=64 MMAs (32 cycles each) is paced by the accumulator
-//                    round trip (~55 cycles, measured: tensor pipe 58 % busy).
+//     are compiled (template ACC_N); measured on B200 (scripts/mma_rate.cu, scripts/ldtm_rate.cu):
+//     a tcgen05.mma with A in TMEM costs N/2 + ~11 cycles whatever the accumulator chaining
+//     (N=64: 43.5 cycles = 73.5 % of nominal, N=128: 74 = 86.5 %, N=256: 138 = 92.7 %).
+//       ACC_N = 64 (default): two 64-row accumulators, the MMA of tile t+1 overlaps the epilogue of
+//                    tile t. Ceiling 73.5 % of the nominal tensor rate per clock.
+//       ACC_N = 128: one 128-row accumulator; faster instructions but the epilogue drain and both
+//                    barrier hand-offs are exposed once per tile (measured slower end to end:
+//                    56.0k vs 68.9k queries/s on the 10M x 768 workload).
+//     A wider double-buffered accumulator does not fit: the stationary 128 x 768 bf16 query tile
+//     alone needs 384 of the 512 TMEM columns.
 //   * epilogue: thread <-> query. Each thread pulls its lane's ACC_N scores (tcgen05.ld 32x32b),
 //     releases the accumulator, takes one max over them and compares with its running k-th best;
 //     only when something beats it (rare after warm-up) does it walk the values and insert

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -185,6 +186,7 @@ static int set_kernel_attrs(mips_index_s* h) {
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT))
   TC_ATTR(false, 128, 3); TC_ATTR(true, 128, 3); TC_ATTR(false, 128, 2); TC_ATTR(true, 128, 2);
   TC_ATTR(false, 64, 6);  TC_ATTR(true, 64, 6);  TC_ATTR(false, 64, 4);  TC_ATTR(true, 64, 4);
+  TC_ATTR(false, 64, 3);  TC_ATTR(false, 64, 12); TC_ATTR(false, 64, 2);
 #undef TC_ATTR
   h->attrs_set = true;
   return 0;
@@ -491,7 +493,11 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     p.n_tiles = n_tiles;
     p.n_qtiles = n_qtiles;
     p.n_splits = n_splits;
-    const int skch = tc::pick_skch(h->d_pad, acc_n);
+    int skch = tc::pick_skch(h->d_pad, acc_n);
+    if (const char* e = getenv("MIPS_TC_SKCH")) {   // tuning experiments only (IP metric, 64-row accumulators)
+      const int v = atoi(e);
+      if (acc_n == 64 && !l2 && (v == 2 || v == 3 || v == 4 || v == 6 || v == 12)) skch = v;
+    }
     p.stages = tc::pick_stages(k, skch, acc_n);
     // a bank tile is re-read by the other query tiles from L2; with one query tile it is dead
     p.cache_hint = n_qtiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
@@ -505,7 +511,11 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     if (acc_n == 128) {
       if (skch == 3) TC_LAUNCH(128, 3, h->tmap128); else TC_LAUNCH(128, 2, h->tmap128);
     } else {
-      if (skch == 6) TC_LAUNCH(64, 6, h->tmap64); else TC_LAUNCH(64, 4, h->tmap64);
+      if (skch == 6) TC_LAUNCH(64, 6, h->tmap64);
+      else if (skch == 12) tc::search_tc_kernel<false, 64, 12><<<grid, tc::THREADS, smem, st>>>(h->tmap64, p);
+      else if (skch == 3) tc::search_tc_kernel<false, 64, 3><<<grid, tc::THREADS, smem, st>>>(h->tmap64, p);
+      else if (skch == 2) tc::search_tc_kernel<false, 64, 2><<<grid, tc::THREADS, smem, st>>>(h->tmap64, p);
+      else TC_LAUNCH(64, 4, h->tmap64);
     }
 #undef TC_LAUNCH
     LAUNCH_CHECK("search_tc_kernel");
