@@ -43,6 +43,8 @@ typedef struct mips_index_s* mips_handle;
 #define MIPS_ALGO_TC 2     /* tcgen05/TMEM/TMA kernel, bf16 bank, d_pad <= 768:
                               2 x 64-row double-buffered TMEM accumulators (default) */
 #define MIPS_ALGO_TC128 3  /* same kernel, one 128-row accumulator (A/B comparison) */
+#define MIPS_ALGO_TC2 4    /* CTA-pair kernel (tcgen05 cta_group::2, M=256 x N=128), bf16 bank,
+                              d_pad <= 1024: 2 x 128-row accumulators, bank tile shared by the pair */
 
 /* Output transform applied by the merge kernel to the ranking key. */
 #define MIPS_OUT_IP 0      /* D = <q,x>                    descending (IndexFlatIP)          */

@@ -15,7 +15,7 @@ _HEADER = Path(__file__).resolve().parent.parent / "include" / "mips_b200.h"
 
 METRIC_IP, METRIC_L2 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128 = 0, 1, 2, 3
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2 = 0, 1, 2, 3, 4
 OUT_IP, OUT_L2, OUT_AUGL2 = 0, 1, 2
 MAX_K = 64
 

@@ -17,6 +17,7 @@
 #include "k0_rows.cuh"
 #include "k1_simt.cuh"
 #include "k1_tc.cuh"
+#include "k1_tc2.cuh"
 #include "k2_merge.cuh"
 #include "mips_b200.h"
 
@@ -62,6 +63,11 @@ struct mips_index_s {
   CUtensorMap tmap128;   // 128-row boxes (single 128-wide accumulator kernel)
   CUtensorMap tmap64;    // 64-row boxes (double-buffered 64-wide accumulator kernel)
   bool tmap_valid = false;
+  // TMA descriptor of the prepared queries (128-row boxes; CTA-pair kernel), re-encoded when the
+  // scratch allocation or its padded row count changes
+  CUtensorMap tmap_q;
+  const void* tmap_q_ptr = nullptr;
+  int tmap_q_rows = 0;
   // scratch (grown on demand; stable after warm-up)
   void* q_prep = nullptr;      size_t q_prep_bytes = 0;
   float* q_norm2 = nullptr;    size_t q_norm2_bytes = 0;
@@ -120,7 +126,7 @@ static size_t elem_bytes(const mips_index_s* h) { return h->dtype == MIPS_DTYPE_
 
 static int encode_bank_tmap(mips_index_s* h) {
   h->tmap_valid = false;
-  if (h->dtype != MIPS_DTYPE_BF16 || h->d_pad > tc::MAX_DPAD) return 0;
+  if (h->dtype != MIPS_DTYPE_BF16 || h->d_pad > tc2::MAX_KCH * tc2::KCH) return 0;
   encode_tiled_fn fn = get_encode_fn();
   if (!fn) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->d_pad), static_cast<cuuint64_t>(h->capacity)};
@@ -134,6 +140,23 @@ static int encode_bank_tmap(mips_index_s* h) {
     if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
   }
   h->tmap_valid = true;
+  return 0;
+}
+
+static int encode_query_tmap(mips_index_s* h, int rows) {
+  if (h->tmap_q_ptr == h->q_prep && h->tmap_q_rows == rows) return 0;
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->d_pad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(h->d_pad) * 2};
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint32_t box[2] = {tc2::KCH, tc2::BLOCK_M};
+  CUresult r = fn(&h->tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->q_prep, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled(queries) failed: %d", (int)r);
+  h->tmap_q_ptr = h->q_prep;
+  h->tmap_q_rows = rows;
   return 0;
 }
 
@@ -188,6 +211,12 @@ static int set_kernel_attrs(mips_index_s* h) {
   TC_ATTR(false, 64, 6);  TC_ATTR(true, 64, 6);  TC_ATTR(false, 64, 4);  TC_ATTR(true, 64, 4);
   TC_ATTR(false, 64, 3);  TC_ATTR(false, 64, 12); TC_ATTR(false, 64, 2);
 #undef TC_ATTR
+#define TC2_ATTR(L2, K)                                                                        \
+  CUDA_TRY(cudaFuncSetAttribute(tc2::search_tc2_kernel<L2, K>,                                 \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_LIMIT))
+  TC2_ATTR(false, 4); TC2_ATTR(true, 4); TC2_ATTR(false, 6); TC2_ATTR(true, 6);
+  TC2_ATTR(false, 2); TC2_ATTR(true, 2);
+#undef TC2_ATTR
   h->attrs_set = true;
   return 0;
 }
@@ -442,7 +471,7 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
                         cudaStream_t st) {
   int rc;
   const size_t eb = elem_bytes(h);
-  const int nq_pad = round_up_i(nq, tc::BLOCK_M);
+  const int nq_pad = round_up_i(nq, algo == MIPS_ALGO_TC2 ? tc2::PAIR_M : tc::BLOCK_M);
   rc = grow(&h->q_prep, &h->q_prep_bytes, static_cast<size_t>(nq_pad) * h->d_pad * eb);
   if (rc) return rc;
   rc = grow(&h->q_norm2, &h->q_norm2_bytes, static_cast<size_t>(nq_pad) * sizeof(float));
@@ -469,7 +498,57 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
   const int slot = h->prof_n % kProfSlots;
   if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
 
-  if (use_tc) {
+  if (algo == MIPS_ALGO_TC2) {
+    rc = encode_query_tmap(h, nq_pad);
+    if (rc) return rc;
+    const int n_tiles = static_cast<int>((h->ntotal + tc2::TILE_N - 1) / tc2::TILE_N);
+    const int n_qpairs = nq_pad / tc2::PAIR_M;
+    const int n_splits = std::max(1, std::min((h->sm_count / 2) / n_qpairs, n_tiles));
+    n_parts = n_splits;
+    const size_t pk = static_cast<size_t>(n_parts) * nq * k;
+    rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+    if (rc) return rc;
+    rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
+    if (rc) return rc;
+    tc2::Params p;
+    p.q = static_cast<const __nv_bfloat16*>(h->q_prep);
+    p.xnorm2 = h->norm2;
+    p.ignore_local = ign_local;
+    p.part_key = h->part_key;
+    p.part_ids = h->part_ids;
+    p.ntotal = h->ntotal;
+    p.nq = nq;
+    p.d_pad = h->d_pad;
+    p.k = k;
+    p.n_tiles = n_tiles;
+    p.n_qpairs = n_qpairs;
+    p.n_splits = n_splits;
+    p.epi_mode = 0;
+    p.probe_mode = 0;
+    if (const char* e = getenv("MIPS_TC2_EPI")) p.epi_mode = atoi(e);
+    if (const char* e = getenv("MIPS_TC2_PROBE")) p.probe_mode = atoi(e);
+    int skch = 4;
+    if (const char* e = getenv("MIPS_TC2_SKCH")) {   // tuning experiments only
+      const int v = atoi(e);
+      if (v == 2 || v == 4 || v == 6) skch = v;
+    }
+    while (skch > 2 && tc2::pick_stages(h->d_pad, k, skch) < 2) skch -= 2;
+    p.stages = tc2::pick_stages(h->d_pad, k, skch);
+    if (p.stages < 2)
+      return set_err(MIPS_E_UNSUPPORTED, "tc2: d_pad=%d with k=%d does not fit shared memory", h->d_pad, k);
+    p.cache_hint = n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+    const size_t smem = tc2::smem_bytes(h->d_pad, k, p.stages, skch);
+    const unsigned grid = static_cast<unsigned>(2 * n_qpairs * n_splits);
+#define TC2_LAUNCH(K)                                                                            \
+  do {                                                                                           \
+    if (l2) tc2::search_tc2_kernel<true, K><<<grid, tc2::THREADS, smem, st>>>(h->tmap64, h->tmap_q, p);  \
+    else    tc2::search_tc2_kernel<false, K><<<grid, tc2::THREADS, smem, st>>>(h->tmap64, h->tmap_q, p); \
+  } while (0)
+    if (skch == 6) TC2_LAUNCH(6); else if (skch == 4) TC2_LAUNCH(4); else TC2_LAUNCH(2);
+#undef TC2_LAUNCH
+    LAUNCH_CHECK("search_tc2_kernel");
+    h->last_algo = "tc2";
+  } else if (use_tc) {
     const int acc_n = algo == MIPS_ALGO_TC128 ? 128 : 64;
     const int n_tiles = static_cast<int>((h->ntotal + acc_n - 1) / acc_n);
     const int n_qtiles = nq_pad / tc::BLOCK_M;
@@ -574,10 +653,19 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tc_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc::MAX_DPAD && h->tmap_valid;
-  if (algo == MIPS_ALGO_AUTO) algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
+  const bool tc2_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc2::MAX_KCH * tc2::KCH && h->tmap_valid &&
+                      tc2::pick_stages(h->d_pad, k, 2) >= 2;
+  if (algo == MIPS_ALGO_AUTO) {
+    static const int auto_tc2 = [] { const char* e = getenv("MIPS_AUTO_TC2"); return e ? atoi(e) : 1; }();
+    // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles
+    if (tc2_ok && (auto_tc2 && nq > tc::BLOCK_M || !tc_ok)) algo = MIPS_ALGO_TC2;
+    else algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
+  }
   if ((algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128) && !tc_ok)
     return set_err(MIPS_E_UNSUPPORTED, "tensor-core search needs a bf16 bank with d_pad <= %d", tc::MAX_DPAD);
-  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC128 && algo != MIPS_ALGO_SIMT)
+  if (algo == MIPS_ALGO_TC2 && !tc2_ok)
+    return set_err(MIPS_E_UNSUPPORTED, "CTA-pair tensor-core search needs a bf16 bank with d_pad <= %d (and k small enough for shared memory)", tc2::MAX_KCH * tc2::KCH);
+  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC128 && algo != MIPS_ALGO_TC2 && algo != MIPS_ALGO_SIMT)
     return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
   if (h->ntotal == 0) {
     // faiss semantics on an empty index: ids -1

@@ -9,13 +9,13 @@ import retrieval_augmented_mds_b200 as m
 from oracle import mips_oracle as o
 
 
-def full_tile(d, n=64, nq=128, seed=0, algo="tc"):
+def full_tile(d, n=64, nq=128, seed=0, algo="tc", kmax=64):
     rng = np.random.default_rng(seed)
     xb = o.bf16_round(rng.standard_normal((n, d), dtype=np.float32))
     xq = o.bf16_round(rng.standard_normal((nq, d), dtype=np.float32))
     idx = m.B200FlatIndex(d, 0, dtype="bf16")
     idx.add(xb)
-    k = min(64, n)
+    k = min(kmax, n)
     r = idx.search_ex(torch.from_numpy(xq), k, algo=algo)
     torch.cuda.synchronize()
     ids = r["ids"].cpu().numpy()
@@ -47,10 +47,14 @@ def full_tile(d, n=64, nq=128, seed=0, algo="tc"):
     return not bad.any()
 
 
+ALGOS = tuple(sys.argv[1:]) or ("tc", "tc128", "tc2")
 ok = True
-for algo in ("tc", "tc128"):
-    for d in (64, 128, 256, 320, 768):
-        ok &= full_tile(d, algo=algo)
+for algo in ALGOS:
+    for d in (64, 128, 256, 320, 768) + ((576, 1024) if algo == "tc2" else ()):
+        kmax = 16 if d > 768 else 64
+        ok &= full_tile(d, algo=algo, kmax=kmax)
+        if algo == "tc2":
+            ok &= full_tile(d, n=128, nq=256, algo=algo, kmax=kmax)
     ok &= full_tile(768, n=128, algo=algo)
     ok &= full_tile(192, n=100, nq=37, algo=algo)
 for n in (128, 640, 6400 + 17):
@@ -61,7 +65,7 @@ for n in (128, 640, 6400 + 17):
     idx = m.B200FlatIndex(d, 0, dtype="bf16")
     idx.add(xb)
     b = idx.search_ex(torch.from_numpy(xq), k, algo="simt")
-    for algo in ("tc", "tc128"):
+    for algo in ALGOS:
         a = idx.search_ex(torch.from_numpy(xq), k, algo=algo)
         torch.cuda.synchronize()
         same = (a["ids"] == b["ids"]).float().mean().item()

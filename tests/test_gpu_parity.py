@@ -84,7 +84,7 @@ def test_fp32_search_is_exact(m, metric, n, d, nq, k):
     assert np.array_equal(I, r["ids"]) and np.array_equal(D, r["scores"])
 
 
-@pytest.mark.parametrize("algo", ["tc", "tc128", "simt"])
+@pytest.mark.parametrize("algo", ["tc", "tc128", "tc2", "simt"])
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("n,d,nq,k", [(5000, 96, 37, 8), (20000, 768, 256, 8), (3001, 64, 1, 1),
                                       (777, 256, 130, 33), (4096, 128, 64, 64), (64 * 300 + 5, 768, 300, 5),
@@ -228,7 +228,7 @@ def test_edge_cases(m, dtype):
     assert (I[:, 5:] == -1).all() and np.isposinf(D[:, 5:]).all()
 
 
-@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("bf16", "tc"), ("bf16", "simt")])
+@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("bf16", "tc"), ("bf16", "tc2"), ("bf16", "simt")])
 def test_duplicates_and_ties_resolve_to_lower_id(m, dtype, algo):
     d, n = 128, 3000
     xb, xq = _data(n, d, 20, seed=9, scale_rows=False)
@@ -246,7 +246,7 @@ def test_duplicates_and_ties_resolve_to_lower_id(m, dtype, algo):
     o.check_topk(xb, xq, r["scores"], r["ids"], 0, rtol=RTOL_BF16, D_ref=D_ref, I_ref=I_ref)
 
 
-@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("bf16", "tc")])
+@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("bf16", "tc"), ("bf16", "tc2")])
 def test_ignore_ids_semantics(m, dtype, algo):
     xb, xq = _data(10000, 96, 50, seed=21)
     if dtype == "bf16":
@@ -352,7 +352,7 @@ def test_config3_slice_bf16_recall(m):
         best_s, o_ = cs.topk(k, dim=1)
         best_i = ci.gather(1, o_)
     r = idx.search_ex(xq, k)
-    assert idx.last_algo == "tc"
+    assert idx.last_algo == "tc2"  # AUTO: CTA-pair kernel for batches of more than 128 queries
     ref_sets = [set(row.tolist()) for row in best_i.cpu()]
     got_sets = [set(row.tolist()) for row in r["ids"].cpu()]
     recall = sum(len(a & b) for a, b in zip(ref_sets, got_sets)) / (nq * k)
