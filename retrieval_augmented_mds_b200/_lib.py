@@ -6,6 +6,7 @@ if a compute entry point is called without a B200, the call raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -37,6 +38,9 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.build()
+    override = os.environ.get("MIPS_B200_LIB")   # developer A/B runs: another build of the same ABI
+    if override:
+        path = Path(override)
     L = C.CDLL(str(path))
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     sig = {

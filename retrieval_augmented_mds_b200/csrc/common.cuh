@@ -51,3 +51,64 @@ __device__ __noinline__ float topk_list_insert(float* keys, int* ids, int k, flo
   ids[p] = id;
   return keys[k - 1];
 }
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread top-k SETS (CTA-pair kernel, thread <-> query epilogue).
+// Each query owns an UNSORTED set of KCAP >= k (ordered key, id) pairs in shared memory with the
+// slot of its WORST entry tracked in a register; K2 merges sets by arg-max rounds and does not
+// need them sorted. Keys are order-preserving uint32 images of the fp32 score; unused slots
+// [k, KCAP) hold the never-worst sentinel 0xffffffff and are skipped on output.
+__device__ __forceinline__ uint32_t f32_to_ordered(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(uint32_t u) {
+  return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+__host__ __device__ inline int topk_kcap(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64; }
+
+// Admission: store (sk, id) into the worst slot, then find the new worst entry = the minimum of
+// the composite (key, ~id), i.e. the lowest key and among equal keys the highest id (the last in
+// the (key desc, id asc) order; empty slots carry id 0xffffffff). Straight-line code: the loads
+// of a 16-entry chunk are issued back to back and reduced by a tournament, so an admission costs
+// ~100 cycles per chunk; the sorted insert / dynamic rescan loops it replaces measured 800-1600
+// cycles at k = 32 (ncu source page: ~50 cycles per entry of dependent load-compare-select).
+template <int KCAP>
+__device__ __forceinline__ uint2 topk_replace_fixed(uint2* set, int worst, uint32_t sk, int id) {
+  set[worst] = make_uint2(sk, static_cast<uint32_t>(id));
+  constexpr int CH = KCAP < 16 ? KCAP : 16;
+  unsigned long long best = ~0ull;
+  int best_pos = 0;
+#pragma unroll
+  for (int base = 0; base < KCAP; base += CH) {
+    unsigned long long c[CH];
+    int p[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const uint2 e = set[base + i];
+      c[i] = (static_cast<unsigned long long>(e.x) << 32) | static_cast<uint32_t>(~e.y);
+      p[i] = base + i;
+    }
+#pragma unroll
+    for (int w = 1; w < CH; w <<= 1) {
+#pragma unroll
+      for (int i = 0; i + w < CH; i += 2 * w) {
+        const bool lt = c[i + w] < c[i];
+        c[i] = lt ? c[i + w] : c[i];
+        p[i] = lt ? p[i + w] : p[i];
+      }
+    }
+    if (c[0] < best) {
+      best = c[0];
+      best_pos = p[0];
+    }
+  }
+  return make_uint2(static_cast<uint32_t>(best >> 32), static_cast<uint32_t>(best_pos));
+}
+// returns (worst key after the admission = new threshold, its slot)
+__device__ __noinline__ uint2 topk_replace(uint2* set, int kcap, int worst, uint32_t sk, int id) {
+  if (kcap == 8) return topk_replace_fixed<8>(set, worst, sk, id);
+  if (kcap == 16) return topk_replace_fixed<16>(set, worst, sk, id);
+  if (kcap == 32) return topk_replace_fixed<32>(set, worst, sk, id);
+  return topk_replace_fixed<64>(set, worst, sk, id);
+}

@@ -46,12 +46,12 @@ constexpr int BBOX_BYTES = HALF_N * KCH * 2;    // 8 KiB: one bank box (64 rows 
 constexpr int ABOX_BYTES = BLOCK_M * KCH * 2;   // 16 KiB: one query box (128 rows x 64 k)
 constexpr int N_BARS = 2 * MAX_STAGES + 8;
 
-// shared memory: [align pad 1024][A tail boxes][stages][lists][barriers]
+// shared memory: [align pad 1024][A tail boxes][stages][top-k sets][barriers]
 __host__ __device__ inline int a_smem_kch(int d_pad) {
   const int n = d_pad / KCH - TMEM_KCH;
   return n > 0 ? n : 0;
 }
-__host__ __device__ inline int list_bytes(int k) { return BLOCK_M * k * 8; }
+__host__ __device__ inline int list_bytes(int k) { return BLOCK_M * topk_kcap(k) * 8; }
 inline int pick_stages(int d_pad, int k, int skch) {
   const int avail = SMEM_LIMIT - 1024 - a_smem_kch(d_pad) * ABOX_BYTES - list_bytes(k) - N_BARS * 8;
   int s = avail / (skch * BBOX_BYTES);
@@ -70,21 +70,39 @@ struct Params {
   int* part_ids;
   int64_t ntotal;
   int nq, d_pad, k, n_tiles, n_qpairs, n_splits, stages;
-  int epi_mode, probe_mode;   // tuning experiments (A/B on one box)
   unsigned long long cache_hint;
 };
 
-// One 64-column half of an accumulator tile, already in registers: fold it into the thread's
-// sorted top-k list (shared memory). The list is only touched when a score beats the k-th best.
+// v[c / 32][c % 32] for a run-time column c without spilling the register array to local memory.
+__device__ __forceinline__ uint32_t pick128(const uint32_t (&v)[4][32], int c) {
+  uint32_t r = 0;
+  switch (c) {
+#define MIPS_PICK(I)                  \
+  case I: r = v[0][I]; break;         \
+  case 32 + I: r = v[1][I]; break;    \
+  case 64 + I: r = v[2][I]; break;    \
+  case 96 + I: r = v[3][I]; break;
+    MIPS_PICK(0) MIPS_PICK(1) MIPS_PICK(2) MIPS_PICK(3) MIPS_PICK(4) MIPS_PICK(5) MIPS_PICK(6) MIPS_PICK(7)
+    MIPS_PICK(8) MIPS_PICK(9) MIPS_PICK(10) MIPS_PICK(11) MIPS_PICK(12) MIPS_PICK(13) MIPS_PICK(14) MIPS_PICK(15)
+    MIPS_PICK(16) MIPS_PICK(17) MIPS_PICK(18) MIPS_PICK(19) MIPS_PICK(20) MIPS_PICK(21) MIPS_PICK(22) MIPS_PICK(23)
+    MIPS_PICK(24) MIPS_PICK(25) MIPS_PICK(26) MIPS_PICK(27) MIPS_PICK(28) MIPS_PICK(29) MIPS_PICK(30) MIPS_PICK(31)
+#undef MIPS_PICK
+  }
+  return r;
+}
+
+// One accumulator row (128 scores of this thread's query), already in registers: fold it into the
+// thread's top-k set (shared memory, unsorted, worst slot tracked). Fast path: one max tree against
+// the admission threshold; the set is only touched when a score beats it.
 template <bool kL2>
-__device__ __forceinline__ void fold_half(uint32_t (&v)[2][32], const float* xnorm2, int id0,
-                                          int64_t ntotal, int ign, bool live, float* lk, int* li,
-                                          int k, float& thr) {
+__device__ __forceinline__ void fold_tile(uint32_t (&v)[4][32], const float* xnorm2, int id0,
+                                          int64_t ntotal, int ign, bool live, uint2* set, int kcap,
+                                          float& thr, int& worst) {
   if (kL2) {
     // ranking key for L2: <q,x> - |x|^2/2 (same address for every lane: broadcast loads)
     const float4* xn = reinterpret_cast<const float4*>(xnorm2 + id0);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < 4; ++g) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 t = __ldg(xn + g * 8 + j);
@@ -97,19 +115,36 @@ __device__ __forceinline__ void fold_half(uint32_t (&v)[2][32], const float* xno
   }
   float m = -CUDART_INF_F;
 #pragma unroll
-  for (int g = 0; g < 2; ++g)
+  for (int g = 0; g < 4; ++g)
 #pragma unroll
     for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[g][j]));
-  if (m > thr && live) {
+  if (__builtin_expect(m > thr && live, 0)) {
+    // Slow path, kept SMALL on purpose (an unrolled compare-and-call per column made the kernel
+    // ~95 KB and ncu showed 42 % of its stall samples on instruction fetch): two instructions
+    // per column build a candidate bit mask, then a rolled loop visits the few set bits and
+    // pulls each score out of its register through one switch.
+    uint32_t mk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = __uint_as_float(v[g][j]);
-        if (s > thr) {
-          const int id = id0 + g * 32 + j;
-          if (id < ntotal && id != ign) thr = topk_list_insert(lk, li, k, s, id);
-        }
+      for (int j = 0; j < 32; ++j) mk[g] |= (__uint_as_float(v[g][j]) > thr ? 1u : 0u) << j;
+    unsigned long long todo = (static_cast<unsigned long long>(mk[1]) << 32) | mk[0];
+    unsigned long long later = (static_cast<unsigned long long>(mk[3]) << 32) | mk[2];
+    int base = 0;
+    while (true) {
+      if (todo == 0ull) {
+        if (base != 0 || later == 0ull) break;
+        todo = later;
+        base = 64;
+      }
+      const int c = base + __ffsll(static_cast<long long>(todo)) - 1;
+      todo &= todo - 1;
+      const float s = __uint_as_float(pick128(v, c));
+      const int id = id0 + c;
+      if (s > thr && id < ntotal && id != ign) {
+        const uint2 r = topk_replace(set, kcap, worst, f32_to_ordered(s), id);
+        thr = ordered_to_f32(r.x);
+        worst = static_cast<int>(r.y);
       }
     }
   }
@@ -132,8 +167,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
   const uint32_t a_off = 0;
   const uint32_t st_off = static_cast<uint32_t>(n_akch) * ABOX_BYTES;
   const uint32_t lists_off = st_off + static_cast<uint32_t>(S) * STAGE_BYTES;
-  float* list_key = reinterpret_cast<float*>(gen + lists_off);
-  int* list_id = reinterpret_cast<int*>(gen + lists_off + BLOCK_M * p.k * 4);
+  uint2* lists = reinterpret_cast<uint2*>(gen + lists_off);   // [128 queries][kcap] (ordered key, id)
   const uint32_t bars_off = lists_off + list_bytes(p.k);
   const uint32_t bars = base + bars_off;
   auto full_bar = [&](int i) { return bars + 8u * i; };                       // leader's is used
@@ -251,11 +285,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
           const int nstage = (stage + 1 == S) ? 0 : stage + 1;
           const uint32_t nphase = (stage + 1 == S) ? phase ^ 1u : phase;
           const bool has_next = !(last_tile && last_ks);
-          const bool next_ready = !has_next ? true : p.probe_mode == 0 ? ptx::mbar_test_wait(full_bar(nstage), nphase) : ptx::mbar_try_wait(full_bar(nstage), nphase);
+          const bool next_ready = has_next ? ptx::mbar_test_wait(full_bar(nstage), nphase) : true;
           const int nacc = (it + 1) & 1;
           const uint32_t nacc_par = acc_par(it + 1) ^ 1u;
           const bool probe_acc = last_ks && !last_tile;
-          const bool acc_ready = !probe_acc ? true : p.probe_mode == 0 ? ptx::mbar_test_wait(tempty_bar(nacc), nacc_par) : ptx::mbar_try_wait(tempty_bar(nacc), nacc_par);
+          const bool acc_ready = probe_acc ? ptx::mbar_test_wait(tempty_bar(nacc), nacc_par) : true;
 
           const int nk = min(SKCH, n_kch - ks * SKCH);
           const uint32_t sbase = base + st_off + static_cast<uint32_t>(stage) * STAGE_BYTES;
@@ -317,15 +351,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
       if (lane == 0) ptx::mbar_arrive_cluster(qready_leader);
     }
 
-    float* lk = list_key + row * p.k;
-    int* li = list_id + row * p.k;
-    for (int i = 0; i < p.k; ++i) {
-      lk[i] = -CUDART_INF_F;
-      li[i] = -1;
-    }
+    const int kcap = topk_kcap(p.k);
+    uint2* set = lists + row * kcap;
+    for (int i = 0; i < kcap; ++i)
+      set[i] = i < p.k ? make_uint2(f32_to_ordered(-CUDART_INF_F), 0xffffffffu) : make_uint2(0xffffffffu, 0u);
+    int worst = 0;
+    float thr = -CUDART_INF_F;
     const bool live = qrow < p.nq;
     const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
-    float thr = -CUDART_INF_F;
 
     int it = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++it) {
@@ -334,42 +367,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
       __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent insert path
       ptx::tc_fence_after();
       const int id0 = tile * TILE_N;
-      if (p.epi_mode == 0) {
-        // the whole 128-column accumulator row goes to registers at once (the CTA has 341 registers
-        // per thread to spend) so that the accumulator is handed back before any top-k work
-        uint32_t v[2][2][32];
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N, v[0][0]);
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 32, v[0][1]);
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 64, v[1][0]);
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 96, v[1][1]);
-        ptx::tmem_wait_ld();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(tempty0_leader + 8u * acc);   // accumulator is in registers
-        fold_half<kL2>(v[0], p.xnorm2, id0, p.ntotal, ign, live, lk, li, p.k, thr);
-        fold_half<kL2>(v[1], p.xnorm2, id0 + 64, p.ntotal, ign, live, lk, li, p.k, thr);
-      } else {
-        uint32_t v[2][32];
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N, v[0]);
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 32, v[1]);
-        ptx::tmem_wait_ld();
-        fold_half<kL2>(v, p.xnorm2, id0, p.ntotal, ign, live, lk, li, p.k, thr);
-        __syncwarp();
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 64, v[0]);
-        ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 96, v[1]);
-        ptx::tmem_wait_ld();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(tempty0_leader + 8u * acc);
-        fold_half<kL2>(v, p.xnorm2, id0 + 64, p.ntotal, ign, live, lk, li, p.k, thr);
-      }
+      // the whole 128-column accumulator row goes to registers at once (the CTA has 341 registers
+      // per thread to spend) so that the accumulator is handed back before any top-k work
+      uint32_t v[4][32];
+      ptx::tmem_ld_x32(lane_addr + acc * TILE_N, v[0]);
+      ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 32, v[1]);
+      ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 64, v[2]);
+      ptx::tmem_ld_x32(lane_addr + acc * TILE_N + 96, v[3]);
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty0_leader + 8u * acc);   // accumulator is in registers
+      fold_tile<kL2>(v, p.xnorm2, id0, p.ntotal, ign, live, set, kcap, thr, worst);
     }
 
     if (live) {
       const size_t o = (static_cast<size_t>(split) * p.nq + qrow) * p.k;
-      for (int i = 0; i < p.k; ++i) {
-        p.part_key[o + i] = lk[i];
-        p.part_ids[o + i] = li[i];
+      for (int i = 0; i < p.k; ++i) {   // unsorted: K2 merges by arg-max rounds
+        const uint2 e = set[i];
+        p.part_key[o + i] = ordered_to_f32(e.x);
+        p.part_ids[o + i] = static_cast<int>(e.y);
       }
     }
   }

@@ -523,10 +523,6 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     p.n_tiles = n_tiles;
     p.n_qpairs = n_qpairs;
     p.n_splits = n_splits;
-    p.epi_mode = 0;
-    p.probe_mode = 0;
-    if (const char* e = getenv("MIPS_TC2_EPI")) p.epi_mode = atoi(e);
-    if (const char* e = getenv("MIPS_TC2_PROBE")) p.probe_mode = atoi(e);
     int skch = 4;
     if (const char* e = getenv("MIPS_TC2_SKCH")) {   // tuning experiments only
       const int v = atoi(e);
