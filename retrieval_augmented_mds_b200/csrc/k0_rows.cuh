@@ -56,8 +56,80 @@ __global__ void __launch_bounds__(256) ingest_rows_kernel(const float* x, int64_
   ss_stored = warp_sum(ss_stored);
   if (lane == 0) {
     if (norm2_out) norm2_out[row] = ss_stored;
-    // non-negative floats order like their bit patterns
-    if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(ss));
+    // non-negative floats order like their bit patterns; the running max only ever grows, so a
+    // stale read can only cause a redundant atomic, never a missed one
+    if (max_norm2_bits && __float_as_uint(ss) > *reinterpret_cast<volatile unsigned int*>(max_norm2_bits))
+      atomicMax(max_norm2_bits, __float_as_uint(ss));
+  }
+}
+
+// Vectorised variant for the common shapes (d % 4 == 0, d <= 128 * NV, 16-byte aligned rows):
+// one warp per row, the row is read ONCE with 16-byte loads and held in registers between the
+// norm pass and the store pass (the scalar kernel reads it twice with 4-byte loads: measured
+// 2.3 TB/s = 35 % of the copy peak on 10M x 768 fp32 -> bf16). Stores are 16 bytes (fp32) or
+// 8 bytes (4 bf16) per lane. Same arithmetic order per element as the scalar kernel except the
+// lane-to-element assignment of the sums (fp32 partial sums regroup; |x|^2 differs in the last bits).
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) ingest_rows_vec_kernel(const float* x, int64_t n, int64_t n_pad,
+                                                              int d, int d_pad, int normalize, T* out,
+                                                              float* __restrict__ norm2_out,
+                                                              unsigned int* __restrict__ max_norm2_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  T* dst = out + row * d_pad;
+  const int nv = d >> 2, nv_pad = d_pad >> 2;   // float4 groups in the row / in the padded row
+  float4 r[NV];
+  float ss = 0.f;
+  if (row < n) {
+    const float4* src = reinterpret_cast<const float4*>(x + row * d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      r[i] = c < nv ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss = fmaf(r[i].x, r[i].x, ss);
+      ss = fmaf(r[i].y, r[i].y, ss);
+      ss = fmaf(r[i].z, r[i].z, ss);
+      ss = fmaf(r[i].w, r[i].w, ss);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  ss = warp_sum(ss);
+  const float scale = (normalize && ss > 0.f) ? (1.0f / sqrtf(ss)) : 1.0f;
+  float ss_stored = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv_pad) {
+      const T t0 = from_f32<T>(r[i].x * scale), t1 = from_f32<T>(r[i].y * scale);
+      const T t2 = from_f32<T>(r[i].z * scale), t3 = from_f32<T>(r[i].w * scale);
+      const float f0 = to_f32<T>(t0), f1 = to_f32<T>(t1), f2 = to_f32<T>(t2), f3 = to_f32<T>(t3);
+      ss_stored = fmaf(f0, f0, ss_stored);
+      ss_stored = fmaf(f1, f1, ss_stored);
+      ss_stored = fmaf(f2, f2, ss_stored);
+      ss_stored = fmaf(f3, f3, ss_stored);
+      if (sizeof(T) == 4) {
+        reinterpret_cast<float4*>(dst)[c] = make_float4(f0, f1, f2, f3);
+      } else {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(dst)[c] = pk;
+      }
+    }
+  }
+  ss_stored = warp_sum(ss_stored);
+  if (lane == 0) {
+    if (norm2_out) norm2_out[row] = row < n ? ss_stored : 0.f;
+    // One atomic per row on a single address serialises in L2 (measured: the kernel sat at 35 % of
+    // the copy peak whatever the load width). The running max only ever grows, so compare with a
+    // plain read first: a stale value can only cause a redundant atomic, never a missed one.
+    if (max_norm2_bits && row < n &&
+        __float_as_uint(ss) > *reinterpret_cast<volatile unsigned int*>(max_norm2_bits))
+      atomicMax(max_norm2_bits, __float_as_uint(ss));
   }
 }
 

@@ -71,6 +71,8 @@ struct Params {
   int64_t ntotal;
   int nq, d_pad, k, n_tiles, n_qpairs, n_splits, stages;
   unsigned long long cache_hint;
+  int* pace;        // [n_splits, n_qpairs] tiles issued so far by each pair (zeroed before the launch), or null
+  int pace_window;  // a pair never runs more than this many tiles ahead of the slowest pair of its split
 };
 
 // v[c / 32][c % 32] for a run-time column c without spilling the register array to local memory.
@@ -232,10 +234,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
     }
     int stage = 0;
     uint32_t phase = 0;
+    // Lock-step pacing. The n_qpairs pairs of one split stream the SAME bank tiles; nothing else
+    // keeps them together, and once they drift apart by more than L2 holds (126 MB over 18 splits
+    // = ~36 tiles) every pair fetches its tiles from HBM again (ncu: 40 GB read per launch for a
+    // 15.4 GB bank, L2 hit rate 41 %). The leader's producer publishes its tile count and does not
+    // run more than `pace_window` tiles ahead of the slowest pair of its split. The wait is
+    // bounded: pacing is a locality hint, never a correctness dependency between CTAs.
+    int* pace_mine = p.pace ? p.pace + split * p.n_qpairs + qpair : nullptr;
+    const int* pace_peer = (p.pace && lane < p.n_qpairs) ? p.pace + split * p.n_qpairs + lane : nullptr;
+    const bool pacing = p.pace != nullptr && rank == 0 && p.n_qpairs > 1;
+    int peer_seen = 0;   // peers' tile counts, loaded while the previous tile's stages were being issued
     for (int tile = tile0; tile < tile1; ++tile) {
       const int row0 = tile * TILE_N + static_cast<int>(rank) * HALF_N;
       for (int ks = 0; ks < n_kstages; ++ks) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (pacing && ks == 0) {
+          // the counters were requested a tile ago (their latency hid behind the wait above); only a
+          // pair that is actually too far ahead pays for fresh loads
+          const int done = tile - tile0;
+          if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(pace_mine), "r"(done) : "memory");
+          int slowest = __reduce_min_sync(0xffffffffu, pace_peer ? peer_seen : 0x7fffffff);
+          for (int spin = 0; done - slowest > p.pace_window && spin < 256; ++spin) {
+            __nanosleep(200);
+            int other = 0x7fffffff;
+            if (pace_peer) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(other) : "l"(pace_peer) : "memory");
+            slowest = __reduce_min_sync(0xffffffffu, other);
+          }
+        }
         const int nk = min(SKCH, n_kch - ks * SKCH);
         const uint32_t dst = base + st_off + static_cast<uint32_t>(stage) * STAGE_BYTES;
         if (ptx::elect_one()) {
@@ -253,7 +278,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
           phase ^= 1u;
         }
       }
+      if (pacing && pace_peer)
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(peer_seen) : "l"(pace_peer) : "memory");
     }
+    if (pacing && lane == 0)
+      asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(pace_mine), "r"(0x7fffffff) : "memory");
     // tail: every multicast "stage free" signal addressed to this CTA has landed before it exits
     for (int i = 0; i < S; ++i) {
       ptx::mbar_wait(empty_bar(stage), phase ^ 1u);

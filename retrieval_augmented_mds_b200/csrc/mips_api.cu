@@ -74,6 +74,7 @@ struct mips_index_s {
   float* part_key = nullptr;   size_t part_key_bytes = 0;
   int* part_ids = nullptr;     size_t part_ids_bytes = 0;
   int* ign_local = nullptr;    size_t ign_bytes = 0;
+  int* pace = nullptr;         size_t pace_bytes = 0;
   float* stage_x = nullptr;    size_t stage_x_bytes = 0;
   // host-call scratch
   float* hq = nullptr;         size_t hq_bytes = 0;
@@ -273,7 +274,7 @@ int mips_destroy(mips_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* dev[] = {h->bank, h->norm2, h->max_norm2_bits, h->q_prep, h->q_norm2, h->part_key,
-                 h->part_ids, h->ign_local, h->stage_x, h->hq, h->hign, h->hkey, h->hids,
+                 h->part_ids, h->ign_local, h->pace, h->stage_x, h->hq, h->hign, h->hkey, h->hids,
                  h->hxn2, h->hqn2, h->hD, h->hI};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -343,6 +344,25 @@ static int launch_ingest(mips_index_s* h, const float* x_dev, int64_t n, int64_t
                          void* out, float* norm2_out, unsigned int* maxbits, cudaStream_t st) {
   const unsigned blocks = static_cast<unsigned>((n_pad + 7) / 8);
   if (blocks == 0) return 0;
+  // vector path: 16-byte loads need d % 4 == 0 and 16-byte aligned rows on both sides
+  const bool vec_ok = h->d % 4 == 0 && h->d_pad <= 1024 && reinterpret_cast<uintptr_t>(x_dev) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(out) % 16 == 0 && !getenv("MIPS_K0_SCALAR");
+  if (vec_ok) {
+#define K0_VEC(T, NV)                                                                                \
+  ingest_rows_vec_kernel<T, NV><<<blocks, 256, 0, st>>>(x_dev, n, n_pad, h->d, h->d_pad, normalize,  \
+                                                        static_cast<T*>(out), norm2_out, maxbits)
+    const int nvl = (h->d_pad / 4 + 31) / 32;   // float4 groups per lane
+    if (h->dtype == MIPS_DTYPE_BF16) {
+      if (nvl <= 2) K0_VEC(__nv_bfloat16, 2); else if (nvl <= 4) K0_VEC(__nv_bfloat16, 4);
+      else if (nvl <= 6) K0_VEC(__nv_bfloat16, 6); else K0_VEC(__nv_bfloat16, 8);
+    } else {
+      if (nvl <= 2) K0_VEC(float, 2); else if (nvl <= 4) K0_VEC(float, 4);
+      else if (nvl <= 6) K0_VEC(float, 6); else K0_VEC(float, 8);
+    }
+#undef K0_VEC
+    LAUNCH_CHECK("ingest_rows_vec_kernel");
+    return 0;
+  }
   if (h->dtype == MIPS_DTYPE_BF16)
     ingest_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
         x_dev, n, n_pad, h->d, h->d_pad, normalize, static_cast<__nv_bfloat16*>(out), norm2_out, maxbits);
@@ -533,6 +553,16 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     if (p.stages < 2)
       return set_err(MIPS_E_UNSUPPORTED, "tc2: d_pad=%d with k=%d does not fit shared memory", h->d_pad, k);
     p.cache_hint = n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+    p.pace = nullptr;
+    p.pace_window = 6;   // measured: HBM reads 40 GB -> ~19 GB per launch on the 10M x 768 bank; step time within +-4 % of unpaced (which side wins depends on how hard the board is power-capped)
+    if (const char* e = getenv("MIPS_TC2_PACE")) p.pace_window = atoi(e);   // tuning; <= 0 disables
+    if (n_qpairs > 1 && p.pace_window > 0) {
+      const size_t pb = static_cast<size_t>(n_splits) * n_qpairs * sizeof(int);
+      rc = grow(&h->pace, &h->pace_bytes, pb);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemsetAsync(h->pace, 0, pb, st));
+      p.pace = h->pace;
+    }
     const size_t smem = tc2::smem_bytes(h->d_pad, k, p.stages, skch);
     const unsigned grid = static_cast<unsigned>(2 * n_qpairs * n_splits);
 #define TC2_LAUNCH(K)                                                                            \
