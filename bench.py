@@ -307,7 +307,7 @@ def main() -> None:
     ap.add_argument("--rows", type=int, default=N_ROWS, help="bank rows (default: the BASELINE workload)")
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--k", type=int, default=TOPK)
-    ap.add_argument("--algo", default="auto", choices=["auto", "tc", "tc128", "tc2", "simt"], help="K1 variant (A/B runs)")
+    ap.add_argument("--algo", default="auto", choices=["auto", "tc", "tc128", "tc2", "tcx", "simt"], help="K1 variant (A/B runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

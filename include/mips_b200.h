@@ -43,6 +43,10 @@ typedef struct mips_index_s* mips_handle;
 #define MIPS_ALGO_TC 2     /* tcgen05/TMEM/TMA kernel, bf16 bank, d_pad <= 768:
                               2 x 64-row double-buffered TMEM accumulators (default) */
 #define MIPS_ALGO_TC128 3  /* same kernel, one 128-row accumulator (A/B comparison) */
+#define MIPS_ALGO_TCX 5    /* fp32 bank, k <= 32, d_pad <= 1024: EXACT search at tensor-core speed — TC2 over
+                              a bf16 shadow of the rows keeps kc > k candidates, their keys are recomputed
+                              from the fp32 rows, a rigorous error bound certifies the top-k, and queries
+                              that fail it (ties at the boundary) are recomputed by SIMT. AUTO on fp32. */
 #define MIPS_ALGO_TC2 4    /* CTA-pair kernel (tcgen05 cta_group::2, M=256 x N=128), bf16 bank,
                               d_pad <= 1024: 2 x 128-row accumulators, bank tile shared by the pair */
 
@@ -156,6 +160,9 @@ const char* mips_last_error(void);
 int64_t mips_launch_count(void);
 /* Name of the search kernel the last mips_search_local call used ("tc" / "simt"). */
 const char* mips_last_algo(mips_handle h);
+/* MIPS_ALGO_TCX statistics: queries (since the last reset) whose exactness certificate failed and
+ * that were recomputed by the SIMT kernel. Sync. */
+int64_t mips_fallback_queries(mips_handle h, int reset);
 /* K1 timing: with profiling on, every search records a CUDA-event pair around its K1 launch on
  * the caller's stream (no sync). mips_k1_ms_total() synchronises on those events and returns the
  * SUM of the K1 durations (ms) recorded since mips_set_profiling(h, 1) (at most 256 launches are

@@ -16,7 +16,7 @@ _HEADER = Path(__file__).resolve().parent.parent / "include" / "mips_b200.h"
 
 METRIC_IP, METRIC_L2 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2 = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2, ALGO_TCX = 0, 1, 2, 3, 4, 5
 OUT_IP, OUT_L2, OUT_AUGL2 = 0, 1, 2
 MAX_K = 64
 
@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
         "mips_last_error": (C.c_char_p, []),
         "mips_launch_count": (i64, []),
         "mips_last_algo": (C.c_char_p, [vp]),
+        "mips_fallback_queries": (i64, [vp, i32]),
         "mips_set_profiling": (i32, [vp, i32]),
         "mips_k1_ms_total": (f32, [vp]),
         "mips_prof_count": (i32, [vp]),

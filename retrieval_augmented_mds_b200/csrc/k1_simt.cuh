@@ -49,7 +49,9 @@ template <typename T, bool kL2>
 __global__ void __launch_bounds__(THREADS, 2) search_simt_kernel(
     const T* __restrict__ q, const T* __restrict__ bank, const float* __restrict__ xnorm2, int nq,
     int64_t ntotal, int d_pad, int k, const int* __restrict__ ignore_local, int n_tiles,
-    float* __restrict__ part_key, int* __restrict__ part_ids) {
+    float* __restrict__ part_key, int* __restrict__ part_ids,
+    const int* __restrict__ tile_active) {   // [n_qtiles] or null: query tiles to (re)compute
+  if (tile_active && !tile_active[blockIdx.x]) return;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);          // [2][BK][BM]
   float* Bs = As + 2 * BK * BM;                            // [2][BK][BN]

@@ -43,18 +43,36 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     float* __restrict__ out_xn2, float* __restrict__ cosine, float* __restrict__ doc_prob,
     float beta, float beta_bias, float* __restrict__ memory_bias, int mem_len,
     const PackedCand* __restrict__ cand_packed,   // !LOCAL: packed input instead of the 3 arrays
-    PackedCand* __restrict__ out_packed) {        // LOCAL: packed output instead of the 3 arrays
+    PackedCand* __restrict__ out_packed,          // LOCAL: packed output instead of the 3 arrays
+    const int* __restrict__ q_active = nullptr,   // only these queries are merged (others keep their outputs)
+    int stage_cap = 0) {                          // LOCAL: shared-memory staging entries per warp (dynamic smem)
   __shared__ float s_key[4][MIPS_MAX_K];
   __shared__ float s_xn2[4][MIPS_MAX_K];
   __shared__ float s_cos[4][MIPS_MAX_K];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 4 + w;
   if (q >= nq) return;
+  if (q_active && !q_active[q]) return;
 
   const int32_t* ids32 = static_cast<const int32_t*>(cand_ids_v);
   const int64_t* ids64 = static_cast<const int64_t*>(cand_ids_v);
   const int64_t ign = ignore_ids ? ignore_ids[q] : -1;
   const int C = n_parts * k_in;
+
+  // LOCAL with many parts (74 splits x 16..64 entries): every round would re-read all C candidates
+  // from global memory (measured 0.39 ms for 256 queries x 2368 candidates). Stage the query's
+  // candidates in shared memory once; the launch provides stage_cap entries per warp (0 = none).
+  extern __shared__ uint2 s_stage[];
+  uint2* stage = nullptr;
+  if (LOCAL && stage_cap >= C && C > 64) {
+    stage = s_stage + static_cast<size_t>(w) * stage_cap;
+    for (int c = lane; c < C; c += 32) {
+      const int p = c / k_in, sidx = c - p * k_in;
+      const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + sidx;
+      stage[c] = make_uint2(__float_as_uint(cand_key[a]), static_cast<uint32_t>(ids32[a]));
+    }
+    __syncwarp();
+  }
 
   float prev_key = CUDART_INF_F;
   int64_t prev_id = -1;
@@ -62,11 +80,20 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
   for (int j = 0; j < k_out; ++j) {
     MergeBest b{-CUDART_INF_F, INT64_MAX, -1};
     for (int c = lane; c < C; c += 32) {
-      const int p = c / k_in, s = c - p * k_in;
-      const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + s;
       int64_t id;
       float key;
-      if (LOCAL) {
+      size_t a = 0;
+      if (LOCAL && stage) {
+        const uint2 e = stage[c];
+        const int32_t l = static_cast<int32_t>(e.y);
+        id = l < 0 ? -1 : id_offset + l;
+        key = __uint_as_float(e.x);
+      } else {
+        const int p = c / k_in, s = c - p * k_in;
+        a = (static_cast<size_t>(p) * nq + q) * k_in + s;
+      }
+      if (LOCAL && stage) {
+      } else if (LOCAL) {
         const int32_t l = ids32[a];
         id = l < 0 ? -1 : id_offset + l;
         key = cand_key[a];

@@ -19,6 +19,7 @@
 #include "k1_tc.cuh"
 #include "k1_tc2.cuh"
 #include "k2_merge.cuh"
+#include "k3_rerank.cuh"
 #include "mips_b200.h"
 
 // ------------------------------------------------------------------------------------------
@@ -56,7 +57,12 @@ struct mips_index_s {
   int64_t ntotal = 0, capacity = 0;
   void* bank = nullptr;
   float* norm2 = nullptr;
-  unsigned int* max_norm2_bits = nullptr;  // device scalar
+  unsigned int* max_norm2_bits = nullptr;  // device scalars: [0] max |x|^2 of the RAW rows (get_phi),
+                                           // [1] max |x|^2 of the STORED rows, [2] max |x - bf16(x)|^2
+  // fp32 index only: bf16 shadow of the rows (tensor-core filter of the exact search, k3_rerank.cuh)
+  __nv_bfloat16* shadow = nullptr;
+  CUtensorMap tmap_shadow64;
+  bool shadow_valid = false;
   float phi = 0.f;
   int sm_count = 148;
   // TMA descriptor of the bank (re-encoded when the allocation changes)
@@ -75,6 +81,13 @@ struct mips_index_s {
   int* part_ids = nullptr;     size_t part_ids_bytes = 0;
   int* ign_local = nullptr;    size_t ign_bytes = 0;
   int* pace = nullptr;         size_t pace_bytes = 0;
+  __nv_bfloat16* q_hi = nullptr; size_t q_hi_bytes = 0;     // bf16-rounded prepared queries
+  float* q_res2 = nullptr;     size_t q_res2_bytes = 0;     // |q - bf16(q)|^2
+  float* cand_key = nullptr;   size_t cand_key_bytes = 0;   // approximate keys of the kc candidates
+  int64_t* cand_rows = nullptr; size_t cand_rows_bytes = 0; // their shard-local rows
+  int* fb_flags = nullptr;     size_t fb_flags_bytes = 0;   // [nq] need_fallback + [ceil(nq/64)] tile flags + [1] counter
+  int64_t fallback_queries = 0;                             // statistics of the last search (host, lazily synced)
+  int* fb_count_dev = nullptr;
   float* stage_x = nullptr;    size_t stage_x_bytes = 0;
   // host-call scratch
   float* hq = nullptr;         size_t hq_bytes = 0;
@@ -125,38 +138,41 @@ static int grow(P** ptr, size_t* cur, size_t need) {
 
 static size_t elem_bytes(const mips_index_s* h) { return h->dtype == MIPS_DTYPE_BF16 ? 2 : 4; }
 
-static int encode_bank_tmap(mips_index_s* h) {
-  h->tmap_valid = false;
-  if (h->dtype != MIPS_DTYPE_BF16 || h->d_pad > tc2::MAX_KCH * tc2::KCH) return 0;
+static int encode_rows_tmap(CUtensorMap* out, void* base, int d_pad, int64_t rows, int box_rows) {
   encode_tiled_fn fn = get_encode_fn();
   if (!fn) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->d_pad), static_cast<cuuint64_t>(h->capacity)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(h->d_pad) * 2};
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d_pad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d_pad) * 2};
   const cuuint32_t estr[2] = {1, 1};
-  for (int rows : {128, 64}) {
-    const cuuint32_t box[2] = {tc::KCH, static_cast<cuuint32_t>(rows)};
-    CUresult r = fn(rows == 128 ? &h->tmap128 : &h->tmap64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->bank,
-                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
-  }
-  h->tmap_valid = true;
+  const cuuint32_t box[2] = {tc::KCH, static_cast<cuuint32_t>(box_rows)};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
   return 0;
 }
 
-static int encode_query_tmap(mips_index_s* h, int rows) {
-  if (h->tmap_q_ptr == h->q_prep && h->tmap_q_rows == rows) return 0;
-  encode_tiled_fn fn = get_encode_fn();
-  if (!fn) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(h->d_pad), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(h->d_pad) * 2};
-  const cuuint32_t estr[2] = {1, 1};
-  const cuuint32_t box[2] = {tc2::KCH, tc2::BLOCK_M};
-  CUresult r = fn(&h->tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->q_prep, gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(MIPS_E_CUDA, "cuTensorMapEncodeTiled(queries) failed: %d", (int)r);
-  h->tmap_q_ptr = h->q_prep;
+static int encode_bank_tmap(mips_index_s* h) {
+  h->tmap_valid = false;
+  h->shadow_valid = false;
+  if (h->d_pad > tc2::MAX_KCH * tc2::KCH) return 0;
+  int rc;
+  if (h->dtype == MIPS_DTYPE_BF16) {
+    if ((rc = encode_rows_tmap(&h->tmap128, h->bank, h->d_pad, h->capacity, 128))) return rc;
+    if ((rc = encode_rows_tmap(&h->tmap64, h->bank, h->d_pad, h->capacity, 64))) return rc;
+    h->tmap_valid = true;
+  } else if (h->shadow) {
+    if ((rc = encode_rows_tmap(&h->tmap_shadow64, h->shadow, h->d_pad, h->capacity, 64))) return rc;
+    h->shadow_valid = true;
+  }
+  return 0;
+}
+
+static int encode_query_tmap(mips_index_s* h, const void* q_bf16, int rows) {
+  if (h->tmap_q_ptr == q_bf16 && h->tmap_q_rows == rows) return 0;
+  int rc = encode_rows_tmap(&h->tmap_q, const_cast<void*>(q_bf16), h->d_pad, rows, tc2::BLOCK_M);
+  if (rc) return rc;
+  h->tmap_q_ptr = q_bf16;
   h->tmap_q_rows = rows;
   return 0;
 }
@@ -175,6 +191,20 @@ static int ensure_capacity(mips_index_s* h, int64_t rows, cudaStream_t st) {
     cudaFree(nb);
     return set_err(MIPS_E_NOMEM, "cudaMalloc norm array: %s", cudaGetErrorString(e));
   }
+  __nv_bfloat16* ns = nullptr;
+  const size_t srow_bytes = static_cast<size_t>(h->d_pad) * 2;
+  if (h->dtype == MIPS_DTYPE_F32 && h->d_pad <= tc2::MAX_KCH * tc2::KCH) {
+    e = cudaMalloc(reinterpret_cast<void**>(&ns), static_cast<size_t>(cap) * srow_bytes);
+    if (e != cudaSuccess) {
+      cudaFree(nb);
+      cudaFree(nn);
+      return set_err(MIPS_E_NOMEM, "cudaMalloc bf16 shadow: %s", cudaGetErrorString(e));
+    }
+    if (h->ntotal > 0 && h->shadow)
+      CUDA_TRY(cudaMemcpyAsync(ns, h->shadow, static_cast<size_t>(h->ntotal) * srow_bytes, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ns) + static_cast<size_t>(h->ntotal) * srow_bytes, 0,
+                             static_cast<size_t>(cap - h->ntotal) * srow_bytes, st));
+  }
   if (h->ntotal > 0) {
     CUDA_TRY(cudaMemcpyAsync(nb, h->bank, static_cast<size_t>(h->ntotal) * row_bytes,
                              cudaMemcpyDeviceToDevice, st));
@@ -188,6 +218,8 @@ static int ensure_capacity(mips_index_s* h, int64_t rows, cudaStream_t st) {
   CUDA_TRY(cudaStreamSynchronize(st));
   if (h->bank) cudaFree(h->bank);
   if (h->norm2) cudaFree(h->norm2);
+  if (h->shadow) cudaFree(h->shadow);
+  h->shadow = ns;
   h->bank = nb;
   h->norm2 = nn;
   h->capacity = cap;
@@ -212,6 +244,7 @@ static int set_kernel_attrs(mips_index_s* h) {
   TC_ATTR(false, 64, 6);  TC_ATTR(true, 64, 6);  TC_ATTR(false, 64, 4);  TC_ATTR(true, 64, 4);
   TC_ATTR(false, 64, 3);  TC_ATTR(false, 64, 12); TC_ATTR(false, 64, 2);
 #undef TC_ATTR
+  CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 4 * 8));
 #define TC2_ATTR(L2, K)                                                                        \
   CUDA_TRY(cudaFuncSetAttribute(tc2::search_tc2_kernel<L2, K>,                                 \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_LIMIT))
@@ -254,8 +287,9 @@ int mips_create(mips_handle* out, int d, int metric, int dtype, int device, int6
   h->dtype = dtype;
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->max_norm2_bits), sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->max_norm2_bits, 0, sizeof(unsigned int));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->max_norm2_bits), 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->max_norm2_bits, 0, 4 * sizeof(unsigned int));
+  h->fb_count_dev = reinterpret_cast<int*>(h->max_norm2_bits + 3);
   if (e != cudaSuccess) {
     delete h;
     return set_err(MIPS_E_CUDA, "cudaMalloc stats: %s", cudaGetErrorString(e));
@@ -274,7 +308,7 @@ int mips_destroy(mips_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* dev[] = {h->bank, h->norm2, h->max_norm2_bits, h->q_prep, h->q_norm2, h->part_key,
-                 h->part_ids, h->ign_local, h->pace, h->stage_x, h->hq, h->hign, h->hkey, h->hids,
+                 h->part_ids, h->ign_local, h->pace, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->hq, h->hign, h->hkey, h->hids,
                  h->hxn2, h->hqn2, h->hD, h->hI};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -292,7 +326,7 @@ int mips_reset(mips_handle h) {
   CUDA_TRY(cudaSetDevice(h->device));
   h->ntotal = 0;
   h->phi = 0.f;
-  CUDA_TRY(cudaMemset(h->max_norm2_bits, 0, sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(h->max_norm2_bits, 0, 4 * sizeof(unsigned int)));
   return 0;
 }
 
@@ -307,6 +341,14 @@ int mips_set_phi(mips_handle h, float phi) {
 }
 float mips_get_phi(mips_handle h) { return h ? h->phi : 0.f; }
 const char* mips_last_algo(mips_handle h) { return h ? h->last_algo : "none"; }
+int64_t mips_fallback_queries(mips_handle h, int reset) {
+  if (!h) return -1;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+  int v = 0;
+  if (cudaMemcpy(&v, h->fb_count_dev, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (reset) cudaMemset(h->fb_count_dev, 0, sizeof(int));
+  return v;
+}
 
 int mips_set_profiling(mips_handle h, int on) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
@@ -373,6 +415,17 @@ static int launch_ingest(mips_index_s* h, const float* x_dev, int64_t n, int64_t
   return 0;
 }
 
+// fp32 index: bf16 shadow of the freshly stored rows [row0, row0 + n) + running maxima for the
+// exactness certificate (k3_rerank.cuh)
+static int update_shadow(mips_index_s* h, int64_t row0, int64_t n, cudaStream_t st) {
+  if (h->dtype != MIPS_DTYPE_F32 || !h->shadow || n <= 0) return 0;
+  shadow_rows_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(
+      static_cast<const float*>(h->bank) + static_cast<size_t>(row0) * h->d_pad, n, h->d_pad,
+      h->shadow + static_cast<size_t>(row0) * h->d_pad, nullptr, h->max_norm2_bits + 1, h->max_norm2_bits + 2);
+  LAUNCH_CHECK("shadow_rows_kernel");
+  return 0;
+}
+
 int mips_add(mips_handle h, const float* x, int64_t n, int x_on_device, int normalize, void* stream) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
   if (n < 0 || (n > 0 && !x)) return set_err(MIPS_E_INVALID, "bad x / n");
@@ -388,6 +441,7 @@ int mips_add(mips_handle h, const float* x, int64_t n, int x_on_device, int norm
     void* dst = static_cast<uint8_t*>(h->bank) + static_cast<size_t>(h->ntotal) * h->d_pad * eb;
     rc = launch_ingest(h, x, n, n, normalize, dst, h->norm2 + h->ntotal, h->max_norm2_bits, st);
     if (rc) return rc;
+    if ((rc = update_shadow(h, h->ntotal, n, st))) return rc;
     h->ntotal += n;
     return 0;
   }
@@ -403,6 +457,7 @@ int mips_add(mips_handle h, const float* x, int64_t n, int x_on_device, int norm
     void* dst = static_cast<uint8_t*>(h->bank) + static_cast<size_t>(h->ntotal) * h->d_pad * eb;
     rc = launch_ingest(h, h->stage_x, m, m, normalize, dst, h->norm2 + h->ntotal, h->max_norm2_bits, st);
     if (rc) return rc;
+    if ((rc = update_shadow(h, h->ntotal, m, st))) return rc;
     h->ntotal += m;
   }
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -485,53 +540,23 @@ int mips_reconstruct(mips_handle h, int64_t row0, int64_t n, float* out, int out
 }
 
 // ------------------------------------------------------------------------------------------ K1
-static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_normalize,
-                        const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
-                        int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
-                        cudaStream_t st) {
-  int rc;
-  const size_t eb = elem_bytes(h);
-  const int nq_pad = round_up_i(nq, algo == MIPS_ALGO_TC2 ? tc2::PAIR_M : tc::BLOCK_M);
-  rc = grow(&h->q_prep, &h->q_prep_bytes, static_cast<size_t>(nq_pad) * h->d_pad * eb);
-  if (rc) return rc;
-  rc = grow(&h->q_norm2, &h->q_norm2_bytes, static_cast<size_t>(nq_pad) * sizeof(float));
-  if (rc) return rc;
-  // query preparation (_prepare_query, mips.py:368-375): normalise, cast, pad, |q|^2
-  rc = launch_ingest(h, q, nq, nq_pad, q_normalize, h->q_prep, h->q_norm2, nullptr, st);
-  if (rc) return rc;
-  if (out_qnorm2)
-    CUDA_TRY(cudaMemcpyAsync(out_qnorm2, h->q_norm2, static_cast<size_t>(nq) * sizeof(float),
-                             cudaMemcpyDeviceToDevice, st));
-  const int* ign_local = nullptr;
-  if (ignore_ids) {
-    rc = grow(&h->ign_local, &h->ign_bytes, static_cast<size_t>(nq) * sizeof(int));
-    if (rc) return rc;
-    ignore_to_local_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ignore_ids, nq, id_offset, h->ntotal,
-                                                             h->ign_local);
-    LAUNCH_CHECK("ignore_to_local_kernel");
-    ign_local = h->ign_local;
-  }
-
-  const bool l2 = h->metric == MIPS_METRIC_L2;
-  const bool use_tc = algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128;
-  int n_parts = 0;
-  const int slot = h->prof_n % kProfSlots;
-  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
-
-  if (algo == MIPS_ALGO_TC2) {
-    rc = encode_query_tmap(h, nq_pad);
+// K1, CTA-pair tensor-core kernel over a bf16 row matrix described by `tmap_bank` (the bf16 bank, or
+// the bf16 shadow of an fp32 bank). Leaves [n_splits, nq, k] candidate lists in h->part_key / part_ids.
+static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_bfloat16* q_bf16, int nq,
+                      int nq_pad, int k, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out) {
+    int rc = encode_query_tmap(h, q_bf16, nq_pad);
     if (rc) return rc;
     const int n_tiles = static_cast<int>((h->ntotal + tc2::TILE_N - 1) / tc2::TILE_N);
     const int n_qpairs = nq_pad / tc2::PAIR_M;
     const int n_splits = std::max(1, std::min((h->sm_count / 2) / n_qpairs, n_tiles));
-    n_parts = n_splits;
-    const size_t pk = static_cast<size_t>(n_parts) * nq * k;
+    *n_parts_out = n_splits;
+    const size_t pk = static_cast<size_t>(n_splits) * nq * k;
     rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
     if (rc) return rc;
     rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
     if (rc) return rc;
     tc2::Params p;
-    p.q = static_cast<const __nv_bfloat16*>(h->q_prep);
+    p.q = q_bf16;
     p.xnorm2 = h->norm2;
     p.ignore_local = ign_local;
     p.part_key = h->part_key;
@@ -567,12 +592,152 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     const unsigned grid = static_cast<unsigned>(2 * n_qpairs * n_splits);
 #define TC2_LAUNCH(K)                                                                            \
   do {                                                                                           \
-    if (l2) tc2::search_tc2_kernel<true, K><<<grid, tc2::THREADS, smem, st>>>(h->tmap64, h->tmap_q, p);  \
-    else    tc2::search_tc2_kernel<false, K><<<grid, tc2::THREADS, smem, st>>>(h->tmap64, h->tmap_q, p); \
+    if (l2) tc2::search_tc2_kernel<true, K><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p);  \
+    else    tc2::search_tc2_kernel<false, K><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p); \
   } while (0)
     if (skch == 6) TC2_LAUNCH(6); else if (skch == 4) TC2_LAUNCH(4); else TC2_LAUNCH(2);
 #undef TC2_LAUNCH
     LAUNCH_CHECK("search_tc2_kernel");
+    return 0;
+}
+
+// K1, exact fp32-FMA kernel over the stored rows (any dtype). `tile_active` (device, one int per
+// 64-query tile, or null) restricts the launch to the query tiles that need recomputing.
+static int launch_simt(mips_index_s* h, int nq, int k, const int* ign_local, bool l2, const int* tile_active,
+                       cudaStream_t st, int* n_parts_out) {
+  const int n_tiles = static_cast<int>((h->ntotal + simt::BN - 1) / simt::BN);
+  const int n_qtiles = (nq + simt::BM - 1) / simt::BM;
+  const int target_blocks = 4 * h->sm_count;
+  int n_splits = std::max(1, std::min((target_blocks + n_qtiles - 1) / n_qtiles, n_tiles));
+  n_splits = std::min(n_splits, 65535);
+  const int nsub = simt::nsub_for_k(k);
+  const int n_parts = n_splits * nsub;
+  *n_parts_out = n_parts;
+  const size_t pk = static_cast<size_t>(n_parts) * nq * k;
+  int rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+  if (rc) return rc;
+  rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
+  if (rc) return rc;
+  const dim3 grid(n_qtiles, n_splits);
+  const size_t smem = simt::smem_bytes(k);
+#define SIMT_LAUNCH(T, L2)                                                                         \
+  simt::search_simt_kernel<T, L2><<<grid, simt::THREADS, smem, st>>>(                              \
+      static_cast<const T*>(h->q_prep), static_cast<const T*>(h->bank), h->norm2, nq, h->ntotal,   \
+      h->d_pad, k, ign_local, n_tiles, h->part_key, h->part_ids, tile_active)
+  if (h->dtype == MIPS_DTYPE_BF16) {
+    if (l2) SIMT_LAUNCH(__nv_bfloat16, true); else SIMT_LAUNCH(__nv_bfloat16, false);
+  } else {
+    if (l2) SIMT_LAUNCH(float, true); else SIMT_LAUNCH(float, false);
+  }
+#undef SIMT_LAUNCH
+  LAUNCH_CHECK("search_simt_kernel");
+  return 0;
+}
+
+// K2 in LOCAL mode: split lists -> one list per query (global ids, |x|^2 gathered). Candidates are
+// staged in shared memory when there are more than a handful per query.
+static int launch_merge_local(mips_index_s* h, const float* part_key, const int* part_ids, const float* bank_xn2,
+                              int n_parts, int nq, int k_in, int k_out, int64_t id_offset, float* out_key,
+                              int64_t* out_ids, float* out_xn2, void* out_packed, const int* q_active,
+                              cudaStream_t st, const char* what) {
+  const int C = n_parts * k_in;
+  int cap = 0;
+  if (C > 64 && C <= 6144) cap = C;
+  const size_t smem = static_cast<size_t>(4) * cap * sizeof(uint2);
+  merge_topk_kernel<true><<<(nq + 3) / 4, 128, smem, st>>>(
+      part_key, part_ids, nullptr, bank_xn2, n_parts, nq, k_in, k_out, id_offset, nullptr, h->metric, MIPS_OUT_IP,
+      0.f, nullptr, out_key, out_ids, out_xn2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
+      static_cast<PackedCand*>(out_packed), q_active, cap);
+  LAUNCH_CHECK(what);
+  return 0;
+}
+
+// candidates kept by the tensor-core filter of the exact search: enough head room between the k-th
+// exact key and the kc-th approximate key for the certificate to hold on non-degenerate data
+static int tcx_candidates(int k) { return std::min(MIPS_MAX_K, std::max(4 * k, k + 16)); }
+// entries each bank split keeps for the filter: a split rarely holds more than a few of the global
+// candidates, and whatever it drops is covered by the certificate (its threshold enters T)
+static int tcx_split_list(int k) { return std::max(k, 16); }
+
+static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_normalize,
+                        const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
+                        int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
+                        cudaStream_t st) {
+  int rc;
+  const size_t eb = elem_bytes(h);
+  const int nq_pad = round_up_i(nq, (algo == MIPS_ALGO_TC2 || algo == MIPS_ALGO_TCX) ? tc2::PAIR_M : tc::BLOCK_M);
+  rc = grow(&h->q_prep, &h->q_prep_bytes, static_cast<size_t>(nq_pad) * h->d_pad * eb);
+  if (rc) return rc;
+  rc = grow(&h->q_norm2, &h->q_norm2_bytes, static_cast<size_t>(nq_pad) * sizeof(float));
+  if (rc) return rc;
+  // query preparation (_prepare_query, mips.py:368-375): normalise, cast, pad, |q|^2
+  rc = launch_ingest(h, q, nq, nq_pad, q_normalize, h->q_prep, h->q_norm2, nullptr, st);
+  if (rc) return rc;
+  if (out_qnorm2)
+    CUDA_TRY(cudaMemcpyAsync(out_qnorm2, h->q_norm2, static_cast<size_t>(nq) * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+  const int* ign_local = nullptr;
+  if (ignore_ids) {
+    rc = grow(&h->ign_local, &h->ign_bytes, static_cast<size_t>(nq) * sizeof(int));
+    if (rc) return rc;
+    ignore_to_local_kernel<<<(nq + 255) / 256, 256, 0, st>>>(ignore_ids, nq, id_offset, h->ntotal,
+                                                             h->ign_local);
+    LAUNCH_CHECK("ignore_to_local_kernel");
+    ign_local = h->ign_local;
+  }
+
+  const bool l2 = h->metric == MIPS_METRIC_L2;
+  const bool use_tc = algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128;
+  int n_parts = 0;
+  const int slot = h->prof_n % kProfSlots;
+  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
+
+  if (algo == MIPS_ALGO_TCX) {
+    // exact fp32 search: tensor-core filter over the bf16 shadow, exact re-rank, certificate, and
+    // the exact SIMT kernel for the query tiles that fail it (k3_rerank.cuh)
+    const int kc = tcx_candidates(k);   // candidates re-ranked per query
+    const int m = tcx_split_list(k);    // entries each split keeps (>= k: a split may hold the whole top-k)
+    const int n_qt = (nq + simt::BM - 1) / simt::BM;
+    if ((rc = grow(&h->q_hi, &h->q_hi_bytes, static_cast<size_t>(nq_pad) * h->d_pad * 2))) return rc;
+    if ((rc = grow(&h->q_res2, &h->q_res2_bytes, static_cast<size_t>(nq_pad) * sizeof(float)))) return rc;
+    if ((rc = grow(&h->cand_key, &h->cand_key_bytes, static_cast<size_t>(nq) * kc * sizeof(float)))) return rc;
+    if ((rc = grow(&h->cand_rows, &h->cand_rows_bytes, static_cast<size_t>(nq) * kc * sizeof(int64_t)))) return rc;
+    if ((rc = grow(&h->fb_flags, &h->fb_flags_bytes, static_cast<size_t>(nq + n_qt) * sizeof(int)))) return rc;
+    int* need_fb = h->fb_flags;
+    int* tile_flag = h->fb_flags + nq;
+    CUDA_TRY(cudaMemsetAsync(tile_flag, 0, static_cast<size_t>(n_qt) * sizeof(int), st));
+    shadow_rows_kernel<<<static_cast<unsigned>((nq_pad + 7) / 8), 256, 0, st>>>(
+        static_cast<const float*>(h->q_prep), nq_pad, h->d_pad, h->q_hi, h->q_res2, nullptr, nullptr);
+    LAUNCH_CHECK("shadow_rows_kernel<queries>");
+    rc = launch_tc2(h, h->tmap_shadow64, h->q_hi, nq, nq_pad, m, ign_local, l2, st, &n_parts);
+    if (rc) return rc;
+    rc = launch_merge_local(h, h->part_key, h->part_ids, nullptr, n_parts, nq, m, kc, 0, h->cand_key, h->cand_rows,
+                            nullptr, nullptr, nullptr, st, "merge_topk_kernel<candidates>");
+    if (rc) return rc;
+#define RERANK(L2)                                                                                         \
+  rerank_exact_kernel<L2><<<nq, 256, 0, st>>>(                                                             \
+      static_cast<const float*>(h->q_prep), static_cast<const float*>(h->bank), h->norm2, h->d_pad,       \
+      h->cand_key, h->cand_rows, nq, kc, k, h->part_key, h->part_ids, n_parts, m, h->q_norm2, h->q_res2,   \
+      h->max_norm2_bits + 1, h->max_norm2_bits + 2, id_offset, out_key, out_ids, out_xnorm2,               \
+      static_cast<PackedCand*>(out_packed), need_fb, tile_flag, h->fb_count_dev)
+    if (l2) RERANK(true); else RERANK(false);
+#undef RERANK
+    LAUNCH_CHECK("rerank_exact_kernel");
+    rc = launch_simt(h, nq, k, ign_local, l2, tile_flag, st, &n_parts);
+    if (rc) return rc;
+    if (h->profiling) {
+      CUDA_TRY(cudaEventRecord(h->ev1[slot], st));
+      h->prof_n++;
+    }
+    rc = launch_merge_local(h, h->part_key, h->part_ids, h->norm2, n_parts, nq, k, k, id_offset, out_key, out_ids,
+                            out_xnorm2, out_packed, need_fb, st, "merge_topk_kernel<fallback>");
+    if (rc) return rc;
+    h->last_algo = "tcx";
+    return 0;
+  }
+  if (algo == MIPS_ALGO_TC2) {
+    rc = launch_tc2(h, h->tmap64, static_cast<const __nv_bfloat16*>(h->q_prep), nq, nq_pad, k, ign_local, l2, st, &n_parts);
+    if (rc) return rc;
     h->last_algo = "tc2";
   } else if (use_tc) {
     const int acc_n = algo == MIPS_ALGO_TC128 ? 128 : 64;
@@ -626,31 +791,8 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     LAUNCH_CHECK("search_tc_kernel");
     h->last_algo = acc_n == 128 ? "tc128" : "tc";
   } else {
-    const int n_tiles = static_cast<int>((h->ntotal + simt::BN - 1) / simt::BN);
-    const int n_qtiles = (nq + simt::BM - 1) / simt::BM;
-    const int target_blocks = 4 * h->sm_count;
-    int n_splits = std::max(1, std::min((target_blocks + n_qtiles - 1) / n_qtiles, n_tiles));
-    n_splits = std::min(n_splits, 65535);
-    const int nsub = simt::nsub_for_k(k);
-    n_parts = n_splits * nsub;
-    const size_t pk = static_cast<size_t>(n_parts) * nq * k;
-    rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+    rc = launch_simt(h, nq, k, ign_local, l2, nullptr, st, &n_parts);
     if (rc) return rc;
-    rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
-    if (rc) return rc;
-    const dim3 grid(n_qtiles, n_splits);
-    const size_t smem = simt::smem_bytes(k);
-#define SIMT_LAUNCH(T, L2)                                                                         \
-  simt::search_simt_kernel<T, L2><<<grid, simt::THREADS, smem, st>>>(                              \
-      static_cast<const T*>(h->q_prep), static_cast<const T*>(h->bank), h->norm2, nq, h->ntotal,   \
-      h->d_pad, k, ign_local, n_tiles, h->part_key, h->part_ids)
-    if (h->dtype == MIPS_DTYPE_BF16) {
-      if (l2) SIMT_LAUNCH(__nv_bfloat16, true); else SIMT_LAUNCH(__nv_bfloat16, false);
-    } else {
-      if (l2) SIMT_LAUNCH(float, true); else SIMT_LAUNCH(float, false);
-    }
-#undef SIMT_LAUNCH
-    LAUNCH_CHECK("search_simt_kernel");
     h->last_algo = "simt";
   }
   if (h->profiling) {
@@ -659,11 +801,9 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
   }
 
   // local k-way merge: split lists -> one list per query, global ids, |x|^2 gathered
-  merge_topk_kernel<true><<<(nq + 3) / 4, 128, 0, st>>>(
-      h->part_key, h->part_ids, nullptr, h->norm2, n_parts, nq, k, k, id_offset, nullptr, h->metric,
-      MIPS_OUT_IP, 0.f, nullptr, out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
-      static_cast<PackedCand*>(out_packed));
-  LAUNCH_CHECK("merge_topk_kernel<local>");
+  rc = launch_merge_local(h, h->part_key, h->part_ids, h->norm2, n_parts, nq, k, k, id_offset, out_key, out_ids,
+                          out_xnorm2, out_packed, nullptr, st, "merge_topk_kernel<local>");
+  if (rc) return rc;
   return 0;
 }
 
@@ -681,6 +821,14 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
   const bool tc_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc::MAX_DPAD && h->tmap_valid;
   const bool tc2_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc2::MAX_KCH * tc2::KCH && h->tmap_valid &&
                       tc2::pick_stages(h->d_pad, k, 2) >= 2;
+  const bool tcx_ok = h->dtype == MIPS_DTYPE_F32 && h->shadow_valid && k <= 32 &&
+                      tc2::pick_stages(h->d_pad, tcx_split_list(k), 2) >= 2;
+  if (algo == MIPS_ALGO_AUTO && h->dtype == MIPS_DTYPE_F32) {
+    static const int auto_tcx = [] { const char* e = getenv("MIPS_AUTO_TCX"); return e ? atoi(e) : 1; }();
+    algo = (tcx_ok && auto_tcx) ? MIPS_ALGO_TCX : MIPS_ALGO_SIMT;
+  }
+  if (algo == MIPS_ALGO_TCX && !tcx_ok)
+    return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d and k <= 32", tc2::MAX_KCH * tc2::KCH);
   if (algo == MIPS_ALGO_AUTO) {
     static const int auto_tc2 = [] { const char* e = getenv("MIPS_AUTO_TC2"); return e ? atoi(e) : 1; }();
     // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles
@@ -691,7 +839,7 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
     return set_err(MIPS_E_UNSUPPORTED, "tensor-core search needs a bf16 bank with d_pad <= %d", tc::MAX_DPAD);
   if (algo == MIPS_ALGO_TC2 && !tc2_ok)
     return set_err(MIPS_E_UNSUPPORTED, "CTA-pair tensor-core search needs a bf16 bank with d_pad <= %d (and k small enough for shared memory)", tc2::MAX_KCH * tc2::KCH);
-  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC128 && algo != MIPS_ALGO_TC2 && algo != MIPS_ALGO_SIMT)
+  if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC128 && algo != MIPS_ALGO_TC2 && algo != MIPS_ALGO_TCX && algo != MIPS_ALGO_SIMT)
     return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
   if (h->ntotal == 0) {
     // faiss semantics on an empty index: ids -1

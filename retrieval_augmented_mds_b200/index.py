@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2, DTYPE_BF16, DTYPE_F32, MAX_K, OUT_AUGL2, OUT_IP,
+from ._lib import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2, ALGO_TCX, DTYPE_BF16, DTYPE_F32, MAX_K, OUT_AUGL2, OUT_IP,
                    OUT_L2, check)
 
 METRIC_INNER_PRODUCT = 0  # faiss.METRIC_INNER_PRODUCT
@@ -23,7 +23,7 @@ METRIC_L2 = 1  # faiss.METRIC_L2
 
 _DTYPES = {"fp32": DTYPE_F32, "float32": DTYPE_F32, "f32": DTYPE_F32, torch.float32: DTYPE_F32,
            "bf16": DTYPE_BF16, "bfloat16": DTYPE_BF16, torch.bfloat16: DTYPE_BF16}
-_ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC, "tc128": ALGO_TC128, "tc2": ALGO_TC2}
+_ALGOS = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC, "tc128": ALGO_TC128, "tc2": ALGO_TC2, "tcx": ALGO_TCX}
 
 
 def _device_index(device) -> int:
@@ -292,6 +292,11 @@ class B200FlatIndex:
     @property
     def last_algo(self) -> str:
         return self._L.mips_last_algo(self._h).decode()
+
+    def fallback_queries(self, reset: bool = True) -> int:
+        """Exact tensor-core search ("tcx", fp32 banks): how many queries failed the exactness
+        certificate since the last reset and were recomputed by the exact SIMT kernel."""
+        return int(self._L.mips_fallback_queries(self._h, int(reset)))
 
 
 def merge_candidates(key: Optional[torch.Tensor], ids: Optional[torch.Tensor], xn2: Optional[torch.Tensor],

@@ -50,9 +50,14 @@ n, d, nq, k = 1_000_000, 768, 256, 8
 idx, t_add = build(n, d, "fp32")
 xq = torch.randn((nq, d), device=dev)
 ms = timed(lambda: idx.search_ex(xq, k), iters=5, warm=2)
+idx.fallback_queries(reset=True)
+idx.search_ex(xq, k)
 out.append({"config": "C2 1Mx768 fp32 nq=256 k=8", "kernel": idx.last_algo, "ms": ms, "qps": nq / ms * 1e3,
-            "tflops_fp32": 2 * nq * n * d / ms / 1e9, "hbm_roofline_ms": n * d * 4 / PEAK_HBM / 1e6,
-            "add_gbs": (n * d * 8) / t_add / 1e6})
+            "fallback_queries": idx.fallback_queries(), "hbm_roofline_ms_fp32_rows": n * d * 4 / PEAK_HBM / 1e6,
+            "hbm_roofline_ms_bf16_shadow": n * d * 2 / PEAK_HBM / 1e6, "add_gbs": (n * d * 10) / t_add / 1e6})
+ms = timed(lambda: idx.search_ex(xq, k, algo="simt"), iters=5, warm=2)
+out.append({"config": "C2 1Mx768 fp32 nq=256 k=8 (plain fp32-FMA kernel)", "kernel": idx.last_algo, "ms": ms,
+            "qps": nq / ms * 1e3, "tflops_fp32": 2 * nq * n * d / ms / 1e9})
 del idx
 # ---- C2 on a bf16 bank (tensor path) for comparison
 idx, t_add = build(n, d, "bf16")

@@ -77,11 +77,51 @@ def test_fp32_search_is_exact(m, metric, n, d, nq, k):
     idx = m.B200FlatIndex(d, metric, dtype="fp32")
     idx.add(xb)
     r = _search_np(idx, xq, k)
-    assert idx.last_algo == "simt"
+    # AUTO on an fp32 bank: tensor-core filter + exact re-rank + certificate for k <= 32, SIMT above
+    assert idx.last_algo == ("tcx" if k <= 32 else "simt")
     n_diff = o.check_topk(xb, xq, r["scores"], r["ids"], metric, rtol=RTOL_F32, what=f"fp32 m{metric}")
     assert n_diff <= max(1, nq * k // 500)
     D, I = idx.search(xq, k)  # numpy in/out = the host end-to-end entry point
     assert np.array_equal(I, r["ids"]) and np.array_equal(D, r["scores"])
+    # the plain fp32-FMA kernel (the fallback of the certificate) gives the same answer
+    s = _search_np(idx, xq, k, algo="simt")
+    assert idx.last_algo == "simt"
+    o.check_topk(xb, xq, s["scores"], s["ids"], metric, rtol=RTOL_F32, what=f"fp32 simt m{metric}")
+    assert (s["ids"] != r["ids"]).mean() <= 2e-3  # only ties inside the fp32 rounding tolerance may differ
+    np.testing.assert_allclose(s["scores"], r["scores"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_fp32_exact_certificate_and_fallback(m, metric):
+    """Exact tensor-core search on an fp32 bank (MIPS_ALGO_TCX): random data certifies without any
+    fallback; exact duplicates straddling the k-th place cannot be certified and go through the
+    SIMT kernel — both give the exact answer with the (score desc, id asc) tie rule."""
+    n, d, nq, k = 30000, 256, 300, 8
+    xb, xq = _data(n, d, nq, seed=77, scale_rows=False)
+    idx = m.B200FlatIndex(d, metric, dtype="fp32")
+    idx.add(xb)
+    idx.fallback_queries(reset=True)
+    r = _search_np(idx, xq, k, algo="tcx")
+    assert idx.last_algo == "tcx"
+    assert idx.fallback_queries() == 0
+    o.check_topk(xb, xq, r["scores"], r["ids"], metric, rtol=RTOL_F32, what="tcx random")
+    # 40 copies of one row: for queries aimed at it the k-th and the kc-th candidates tie exactly
+    xb2 = xb.copy()
+    dup = np.arange(100, 100 + 40 * 700, 700)
+    xb2[dup] = xb2[100]
+    xq2 = xq.copy()
+    xq2[:50] = xb2[100] * 3 + 0.01 * xq[:50]
+    idx2 = m.B200FlatIndex(d, metric, dtype="fp32")
+    idx2.add(xb2)
+    idx2.fallback_queries(reset=True)
+    r2 = _search_np(idx2, xq2, k, algo="tcx")
+    n_fb = idx2.fallback_queries()
+    assert 50 <= n_fb <= nq
+    for q in range(50):
+        assert r2["ids"][q].tolist() == dup[:k].tolist()  # lowest ids among the exact ties
+    o.check_topk(xb2, xq2, r2["scores"], r2["ids"], metric, rtol=RTOL_F32, what="tcx ties")
+    s2 = _search_np(idx2, xq2, k, algo="simt")
+    assert np.array_equal(s2["ids"][:50], r2["ids"][:50])
 
 
 @pytest.mark.parametrize("algo", ["tc", "tc128", "tc2", "simt"])
@@ -228,7 +268,7 @@ def test_edge_cases(m, dtype):
     assert (I[:, 5:] == -1).all() and np.isposinf(D[:, 5:]).all()
 
 
-@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("bf16", "tc"), ("bf16", "tc2"), ("bf16", "simt")])
+@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("fp32", "tcx"), ("bf16", "tc"), ("bf16", "tc2"), ("bf16", "simt")])
 def test_duplicates_and_ties_resolve_to_lower_id(m, dtype, algo):
     d, n = 128, 3000
     xb, xq = _data(n, d, 20, seed=9, scale_rows=False)
@@ -246,7 +286,7 @@ def test_duplicates_and_ties_resolve_to_lower_id(m, dtype, algo):
     o.check_topk(xb, xq, r["scores"], r["ids"], 0, rtol=RTOL_BF16, D_ref=D_ref, I_ref=I_ref)
 
 
-@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("bf16", "tc"), ("bf16", "tc2")])
+@pytest.mark.parametrize("dtype,algo", [("fp32", "simt"), ("fp32", "tcx"), ("bf16", "tc"), ("bf16", "tc2")])
 def test_ignore_ids_semantics(m, dtype, algo):
     xb, xq = _data(10000, 96, 50, seed=21)
     if dtype == "bf16":
