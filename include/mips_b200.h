@@ -171,6 +171,21 @@ int mips_set_profiling(mips_handle h, int on);
 float mips_k1_ms_total(mips_handle h);
 int mips_prof_count(mips_handle h);
 
+/* ---- retrieval metrics (next row N5) ------------------------------------------------------ */
+
+/* Replaces retriever_metrics (reference sotasum/pretrain.py:69-85; copy retriever_lightning.py:71-87)
+ * together with the host loop that builds its hit matrix (sotasum/mips.py:456-463):
+ * pred[b, j] = (row_aid[ids[b, j]] == query_aid[b]) (ids < 0 never hit), then
+ *   out3[0] = mean_b(sum_j pred / counts[b])                         recall
+ *   out3[1] = mean_b(1 / argmax_j pred, inf -> 0)                    reciprocal_rank (the reference's
+ *             own definition: a first hit at index 0 scores 0, like a row without hits)
+ *   out3[2] = mean_b(sum_j (cumsum(pred)_j / (j+1)) * pred_j / counts[b])   average_precision
+ * All pointers are device memory; per_query [nq, 3] is scratch that also returns the per-query
+ * terms; pred_out [nq, k] is optional. k <= MIPS_MAX_K. Async on `stream`. */
+int mips_retriever_metrics(const int64_t* ids, int nq, int k, const int64_t* row_aid, int64_t n_rows,
+                           const int64_t* query_aid, const float* counts, float* per_query, float* out3,
+                           float* pred_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

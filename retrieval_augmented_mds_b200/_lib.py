@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         "mips_launch_count": (i64, []),
         "mips_last_algo": (C.c_char_p, [vp]),
         "mips_fallback_queries": (i64, [vp, i32]),
+        "mips_retriever_metrics": (i32, [vp, i32, i32, vp, i64, vp, vp, vp, vp, vp, vp]),
         "mips_set_profiling": (i32, [vp, i32]),
         "mips_k1_ms_total": (f32, [vp]),
         "mips_prof_count": (i32, [vp]),

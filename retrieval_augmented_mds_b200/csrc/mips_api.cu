@@ -20,6 +20,7 @@
 #include "k1_tc2.cuh"
 #include "k2_merge.cuh"
 #include "k3_rerank.cuh"
+#include "k4_metrics.cuh"
 #include "mips_b200.h"
 
 // ------------------------------------------------------------------------------------------
@@ -960,6 +961,22 @@ int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normal
   CUDA_TRY(cudaMemcpyAsync(D, h->hD, nk * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(I, h->hI, nk * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ metrics
+int mips_retriever_metrics(const int64_t* ids, int nq, int k, const int64_t* row_aid, int64_t n_rows,
+                           const int64_t* query_aid, const float* counts, float* per_query, float* out3,
+                           float* pred_out, void* stream) {
+  if (nq < 0 || k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "bad nq / k (k must be in [1, %d])", MIPS_MAX_K);
+  if (nq == 0) return 0;
+  if (!ids || !row_aid || !query_aid || !counts || !per_query || !out3) return set_err(MIPS_E_INVALID, "null buffers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  retrieval_metrics_rows_kernel<<<(nq + 3) / 4, 128, 0, st>>>(ids, nq, k, row_aid, n_rows, query_aid, counts,
+                                                             per_query, pred_out);
+  LAUNCH_CHECK("retrieval_metrics_rows_kernel");
+  retrieval_metrics_mean_kernel<<<1, 256, 0, st>>>(per_query, nq, out3);
+  LAUNCH_CHECK("retrieval_metrics_mean_kernel");
   return 0;
 }
 

@@ -397,3 +397,31 @@ def normalize_L2(x) -> None:
         raise ValueError("normalize_L2 needs a C-contiguous float32 [n, d] array")
     dev = _device_index(None)
     check(L.mips_normalize_l2(x.ctypes.data_as(C.c_void_p), x.shape[0], x.shape[1], 0, dev, None))
+
+
+def retriever_metrics(ids: torch.Tensor, row_aid: torch.Tensor, query_aid: torch.Tensor, counts: torch.Tensor,
+                      return_pred: bool = False) -> dict:
+    """retriever_metrics (pretrain.py:69-85) + the hit matrix of mips.py:456-463, on the device:
+    ids int64 [B, k] as returned by the search, row_aid int64 [N] (the `aid` of every memory row),
+    query_aid int64 [B], counts float32 [B] (`aid_counts`). Returns python floats like the reference
+    (one 12-byte read back), plus the per-query terms and optionally the hit matrix as CUDA tensors."""
+    if not (ids.is_cuda and row_aid.is_cuda and query_aid.is_cuda and counts.is_cuda):
+        raise ValueError("retriever_metrics runs on the GPU: pass CUDA tensors (no CPU compute path)")
+    if ids.dim() != 2 or ids.dtype != torch.int64:
+        raise ValueError("ids must be int64 [B, k]")
+    B, k = ids.shape
+    dev = ids.device
+    ids, row_aid = ids.contiguous(), row_aid.to(torch.int64).contiguous()
+    query_aid, counts = query_aid.to(torch.int64).contiguous(), counts.to(torch.float32).contiguous()
+    per_q = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    out3 = torch.zeros(3, dtype=torch.float32, device=dev)
+    pred = torch.empty((B, k), dtype=torch.float32, device=dev) if return_pred else None
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(_lib.lib().mips_retriever_metrics(_ptr(ids), B, k, _ptr(row_aid), row_aid.shape[0], _ptr(query_aid),
+                                                _ptr(counts), _ptr(per_q), _ptr(out3), _ptr(pred), st))
+    r, rr, ap = out3.cpu().tolist()
+    out = {"recall": r, "reciprocal_rank": rr, "average_precision": ap, "per_query": per_q}
+    if return_pred:
+        out["pred"] = pred
+    return out

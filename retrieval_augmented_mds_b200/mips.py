@@ -48,8 +48,10 @@ class Mips:
                              f"{self.args.mips_string_factory!r}")
         self.tmp_folder = Path(self.args.mips_tmp_folder)
         self.mips_folder = self.tmp_folder / "mips"
-        self.index_file = self.mips_folder / "index.b200"
+        self.index_file = self.mips_folder / "index.faiss"      # same names as mips.py:162-165
         self.max_norm_file = self.mips_folder / "max_norm.pkl"
+        self.embeddings_folder = self.mips_folder / "embeddings"
+        self.meta_file = self.mips_folder / "b200_meta.json"
         self.string_factory = self.args.mips_string_factory
         self.train_size = self.args.mips_train_size
         self.metric_type = self.args.mips_metric_type
@@ -169,27 +171,92 @@ class Mips:
                   normalize_queries=norm_q, out_mode=out_mode, beta=beta, beta_bias=beta_bias)
 
     # ------------------------------------------------------------------ save / load (mips.py:531-549)
+    def _rank_suffix(self) -> str:
+        w = self._sharded.world if self._sharded is not None else 1
+        return f".rank{self._sharded.rank}of{w}" if w > 1 else ""
+
     def save(self) -> None:
-        """Rank-local checkpoint: stored rows (as float32) + metadata. (Interchange with the
-        reference's index.faiss / Arrow layout is the 'next' row N4 of SURVEY §8f.)"""
-        shutil.rmtree(self.mips_folder, ignore_errors=True)
+        """Checkpoint in the reference's layout (mips.py:531-543): `mips/index.faiss` is the flat faiss
+        file the reference's `load()` reads (faiss_io.py) — IndexFlatIP over the (normalised) rows, or
+        IndexFlatL2 over the AUGMENTED rows [x, sqrt(phi - |x|^2)] (d+1 columns) exactly as
+        `build_index` left them in the reference (mips.py:316-331) — `mips/max_norm.pkl` is a pickled
+        float (cloudpickle.load reads plain pickles) and `mips/embeddings/` is the Arrow dataset with
+        the `embeddings` column (written when `datasets` is importable; text columns are outside the
+        hot path). A row-sharded bank writes one file set per rank (suffix `.rank{r}of{G}`)."""
+        import json
+
+        from . import faiss_io
+
+        sfx = self._rank_suffix()
+        if sfx == "" or self._sharded.rank == 0:
+            shutil.rmtree(self.mips_folder, ignore_errors=True)
         self.mips_folder.mkdir(parents=True, exist_ok=True)
-        rows = self.index.reconstruct_n(0, self.index.ntotal)
-        np.savez(self.index_file, rows=rows, metric_type=self.metric_type, normalize=self.normalize,
-                 phi=np.float32(self.phi if self.phi is not None else 0.0), id_offset=self.index.id_offset,
-                 dtype=self.index.dtype)
-        with open(self.max_norm_file, "wb") as f:
-            pickle.dump(self.max_norm, f)
+        if self._sharded is not None and self._sharded.world > 1:
+            torch.distributed.barrier(self.group)
+        n, d = self.index.ntotal, self.index.d
+        l2 = self.metric_type == METRIC_L2
+
+        def blocks():
+            for i in range(0, n, 262144):
+                rows = self.index.reconstruct_n(i, min(262144, n - i))
+                if l2:   # augment_xb (mips.py:59-65) from the stored |x|^2: the column is never kept in HBM
+                    extra = np.sqrt(np.maximum(np.float32(self.phi) - (rows.astype(np.float32) ** 2).sum(1), 0.0))
+                    rows = np.hstack((rows, extra.reshape(-1, 1).astype(np.float32)))
+                yield rows
+
+        with open(str(self.index_file) + sfx, "wb") as f:
+            faiss_io.write_flat(f.write, blocks(), d + 1 if l2 else d, n, self.metric_type)
+        with open(str(self.max_norm_file) + sfx, "wb") as f:
+            pickle.dump(float(self.max_norm), f)
+        with open(str(self.meta_file) + sfx, "w") as f:
+            json.dump({"bank_dtype": self.index.dtype, "id_offset": int(self.index.id_offset), "d": d,
+                       "metric_type": int(self.metric_type), "normalize": bool(self.normalize),
+                       "phi": None if self.phi is None else float(self.phi)}, f)
+        try:
+            import datasets  # optional: the reference's load() also wants the Arrow `embeddings` folder
+            ds = datasets.Dataset.from_dict({self.embeddings_column: np.concatenate(list(blocks())) if n else np.zeros((0, d), np.float32)})
+            ds.save_to_disk(str(self.embeddings_folder) + sfx)
+        except ImportError:
+            pass
 
     def load(self) -> None:
-        z = np.load(str(self.index_file) + ".npz" if not str(self.index_file).endswith(".npz") else self.index_file,
-                    allow_pickle=False)
-        rows = z["rows"]
-        self.index = B200FlatIndex(rows.shape[1], METRIC_INNER_PRODUCT, dtype=str(z["dtype"]), device=self.device,
-                                   capacity=rows.shape[0], id_offset=int(z["id_offset"]))
-        self.index.add(rows)                            # rows were normalised before they were stored
-        if self.metric_type == METRIC_L2:
-            self.phi = float(z["phi"])
+        """Load `mips/index.faiss` (+ `max_norm.pkl`) written by `save()` OR by the reference
+        (`Dataset.save_faiss_index`, mips.py:536). An L2 file holds augmented rows: the last column is
+        dropped (it is a function of |x|^2 and phi) and phi is recovered as |x~|^2 of the first row."""
+        import json
+
+        from . import faiss_io
+
+        sfx = self._rank_suffix()
+        meta = {}
+        if Path(str(self.meta_file) + sfx).exists():
+            meta = json.loads(Path(str(self.meta_file) + sfx).read_text())
+        with open(str(self.index_file) + sfx, "rb") as f:
+            h = faiss_io.read_flat_header(f.read)
+            l2 = h["metric_type"] == METRIC_L2
+            d_file = h["d"]
+            d = d_file - 1 if l2 else d_file
+            self.index = B200FlatIndex(d, METRIC_INNER_PRODUCT, dtype=meta.get("bank_dtype", self.args.bank_dtype),
+                                       device=self.device, capacity=max(h["ntotal"], 1),
+                                       id_offset=int(meta.get("id_offset", 0)))
+            phi = None
+            left = h["ntotal"]
+            while left > 0:
+                nb = min(262144, left)
+                rows = np.frombuffer(f.read(nb * d_file * 4), dtype="<f4").reshape(nb, d_file)
+                if l2:
+                    if phi is None:
+                        phi = float((rows[0].astype(np.float64) ** 2).sum())
+                    rows = np.ascontiguousarray(rows[:, :d])
+                self.index.add(rows)                    # rows were normalised before they were stored
+                left -= nb
+        self.metric_type = h["metric_type"]
+        if l2:
+            self.phi = float(meta["phi"]) if meta.get("phi") is not None else phi
             self.index.phi = self.phi
-        with open(self.max_norm_file, "rb") as f:
+        if self.group is not None:
+            self._sharded = _sharded.ShardedFlatIndex(self.index, self.group)
+            off, self._sharded.counts = _sharded.exchange_offsets(self.index.ntotal, self.group, self.index.device)
+            self.index.id_offset = off
+        with open(str(self.max_norm_file) + sfx, "rb") as f:
             self.max_norm = pickle.load(f)

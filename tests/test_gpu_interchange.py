@@ -1,0 +1,141 @@
+"""GPU tests of the drop-in routes around the index (SURVEY §8b route 1, §8f N4): the `faiss`
+stand-in under an UNMODIFIED HF `datasets` (the exact call sequence of the reference,
+sotasum/mips.py:333-345, :383-386, :536, :547), the flat `index.faiss` round trip and the
+`Mips.save` / `Mips.load` layout."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import retrieval_augmented_mds_b200 as pkg
+from oracle import mips_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, nq, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, d), dtype=np.float32), rng.standard_normal((nq, d), dtype=np.float32)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_write_read_index_round_trip(cuda_device, metric):
+    xb, xq = _data(3000, 96, 17, 3)
+    idx = pkg.B200FlatIndex(96, metric, dtype="fp32")
+    idx.add(xb)
+    buf = io.BytesIO()
+    pkg.write_index(idx, buf)
+    assert buf.getvalue() == pkg.faiss_io.serialize_rows(xb, metric)      # fp32 rows are stored verbatim
+    back = pkg.read_index(io.BytesIO(buf.getvalue()))
+    assert (back.d, back.ntotal, back.metric_type) == (96, 3000, metric)
+    D0, I0 = idx.search(xq, 5)
+    D1, I1 = back.search(xq, 5)
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+
+
+def test_reference_call_sequence_through_unmodified_datasets(cuda_device, tmp_path):
+    """Mips.build_index / Mips.search / Mips.save / Mips.load as the reference drives HF datasets,
+    with `import faiss` resolving to the stand-in."""
+    pkg.install_faiss_shim()
+    datasets = pytest.importorskip("datasets")
+    import faiss
+
+    if "b200" not in faiss.__version__:
+        pytest.skip("a real faiss is installed")
+    xb, xq = _data(2500, 64, 9, 11)
+    xb_n = o.normalize_L2(xb)
+    ds = datasets.Dataset.from_dict({"embeddings": xb_n})
+    ds.set_format("numpy", columns=["embeddings"])
+    ds.add_faiss_index(column="embeddings", index_name="mips_embeddings", string_factory="Flat",
+                       train_size=None, metric_type=faiss.METRIC_INNER_PRODUCT, faiss_verbose=False)
+    index = ds.get_index("mips_embeddings").faiss_index
+    assert isinstance(index, pkg.B200FlatIndex) and index.ntotal == 2500   # added in 1000-row batches
+    index.nprobe = 4                                                         # mips.py:342-345: accepted, ignored
+    q = xq.copy()
+    faiss.normalize_L2(q)                                                    # mips.py:524
+    D, I = index.search(q, 6)                                                # mips.py:383-386
+    D_ref, I_ref = o.exact_topk_f64(xb_n, o.normalize_L2(xq), 6)
+    o.check_topk(xb_n, o.normalize_L2(xq), D, I, 0, rtol=1e-5, D_ref=D_ref, I_ref=I_ref, what="datasets route")
+    scores, examples = ds.get_nearest_examples_batch("mips_embeddings", q, k=3)   # retriever_lightning.py:317-321
+    assert len(examples) == 9 and np.allclose(np.asarray(scores)[:, 0], D[:, 0])
+    f = tmp_path / "index.faiss"
+    ds.save_faiss_index("mips_embeddings", f)                                # mips.py:536
+    assert f.read_bytes()[:4] == b"IxFI"
+    ds.drop_index("mips_embeddings")
+    ds.load_faiss_index("mips_embeddings", f)                                # mips.py:547
+    D2, I2 = ds.get_index("mips_embeddings").faiss_index.search(q, 6)
+    assert np.array_equal(I, I2) and np.array_equal(D, D2)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_mips_facade_save_load_reference_layout(cuda_device, tmp_path, metric):
+    xb, xq = _data(4000, 80, 12, 5 + metric)
+    cfg = pkg.MipsConfig(mips_metric_type=metric, mips_normalize=True, mips_tmp_folder=str(tmp_path), bank_dtype="fp32")
+    mips = pkg.Mips(cfg)
+    mips.build_index(xb)
+    s0, i0 = mips.search(xq, None, 7)
+    mips.save()
+    raw = (tmp_path / "mips" / "index.faiss").read_bytes()
+    h = pkg.faiss_io.read_flat_header(io.BytesIO(raw).read)
+    rows = np.frombuffer(raw, dtype="<f4", offset=45).reshape(h["ntotal"], h["d"])
+    if metric == 0:   # IndexFlatIP over the normalised rows (mips.py:306-314)
+        assert raw[:4] == b"IxFI" and h["d"] == 80
+        np.testing.assert_allclose(rows, o.normalize_L2(xb), rtol=2e-7, atol=1e-8)
+    else:             # IndexFlatL2 over augment_xb(rows, phi) (mips.py:316-331): d + 1 columns
+        assert raw[:4] == b"IxF2" and h["d"] == 81
+        want = o.augment_xb(xb, o.get_phi(xb))
+        assert np.array_equal(rows[:, :80], xb)                      # L2 rows are stored raw (not normalised)
+        # sqrt(phi - |x|^2): for the max-norm row the argument is 0 +- a few ulp of |x|^2 (~1e-5), i.e. ~3e-3
+        np.testing.assert_allclose(rows[:, 80], want[:, 80], rtol=1e-4, atol=2e-2)
+    again = pkg.Mips(cfg)
+    again.load()
+    assert np.isclose(again.max_norm, mips.max_norm)
+    s1, i1 = again.search(xq, None, 7)
+    assert np.array_equal(np.asarray(i0), np.asarray(i1))
+    np.testing.assert_allclose(np.asarray(s0), np.asarray(s1), rtol=1e-5, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------- N5
+def test_retriever_metrics_on_device_match_reference(cuda_device, golden):
+    """Golden hit matrices generated by the reference's own retriever_metrics (pretrain.py:69-85):
+    rebuild ids / labels that produce exactly that hit matrix and compute the metrics on the GPU."""
+    g = golden["retriever_metrics"]
+    pred, counts = g["pred"], g["counts"]
+    B, k = pred.shape
+    rng = np.random.default_rng(1)
+    n_rows = 5000
+    row_aid = rng.integers(1000, 2000, n_rows).astype(np.int64)
+    query_aid = np.arange(B, dtype=np.int64)                 # labels no memory row carries ...
+    ids = rng.permutation(n_rows)[: B * k].reshape(B, k).astype(np.int64)
+    for b in range(B):
+        row_aid[ids[b][pred[b] > 0]] = query_aid[b]          # ... except the rows that must hit
+    r = pkg.retriever_metrics(torch.from_numpy(ids).cuda(), torch.from_numpy(row_aid).cuda(),
+                              torch.from_numpy(query_aid).cuda(), torch.from_numpy(counts).cuda(), return_pred=True)
+    assert np.array_equal(r["pred"].cpu().numpy(), pred)
+    for key in ("recall", "reciprocal_rank", "average_precision"):
+        assert np.isclose(r[key], float(g[key]), rtol=1e-6, atol=1e-7), key
+    want = o.retriever_metrics(pred, counts)
+    assert np.isclose(r["recall"], want["recall"], rtol=1e-6)
+
+
+def test_retriever_metrics_edge_cases(cuda_device):
+    """ids of -1 (k > ntotal padding) never hit; a first-rank hit scores reciprocal rank 0 (the
+    reference's 1/argmax quirk); k up to 64."""
+    ids = torch.tensor([[3, 4, -1, -1], [9, 3, 4, 5], [7, 7, 7, 7]], dtype=torch.int64).cuda()
+    row_aid = torch.arange(10, dtype=torch.int64).cuda() % 5      # aid(row) = row % 5
+    query_aid = torch.tensor([3, 4, 1], dtype=torch.int64).cuda()
+    counts = torch.tensor([2.0, 2.0, 1.0]).cuda()
+    r = pkg.retriever_metrics(ids, row_aid, query_aid, counts, return_pred=True)
+    pred = r["pred"].cpu().numpy()
+    assert pred.tolist() == [[1, 0, 0, 0], [1, 0, 1, 0], [0, 0, 0, 0]]
+    want = o.retriever_metrics(pred, counts.cpu().numpy())
+    for key in want:
+        assert np.isclose(r[key], want[key], rtol=1e-6, atol=1e-7), key
+    assert r["reciprocal_rank"] == 0.0
+    big = torch.randint(0, 10, (5, 64), dtype=torch.int64).cuda()
+    rb = pkg.retriever_metrics(big, row_aid, torch.zeros(5, dtype=torch.int64).cuda(), torch.full((5,), 3.0).cuda(),
+                               return_pred=True)
+    wb = o.retriever_metrics(rb["pred"].cpu().numpy(), np.full(5, 3.0, np.float32))
+    for key in wb:
+        assert np.isclose(rb[key], wb[key], rtol=1e-6, atol=1e-7), key
