@@ -73,6 +73,8 @@ int mips_destroy(mips_handle h);
 /* faiss Index.reset(): drop all rows, keep the allocation. */
 int mips_reset(mips_handle h);
 int64_t mips_ntotal(mips_handle h);
+/* rows the HBM shard can hold without reallocating (double-buffered refresh reuses allocations) */
+int64_t mips_capacity(mips_handle h);
 int mips_dim(mips_handle h);
 int mips_metric(mips_handle h);
 int mips_dtype(mips_handle h);
@@ -185,6 +187,25 @@ int mips_prof_count(mips_handle h);
 int mips_retriever_metrics(const int64_t* ids, int nq, int k, const int64_t* row_aid, int64_t n_rows,
                            const int64_t* query_aid, const float* counts, float* per_query, float* out3,
                            float* pred_out, void* stream);
+
+/* ---- result gather for the consumer (next row N2) ------------------------------------------ */
+
+/* Stored rows of the shard by GLOBAL id as fp32 [n, d] (device): replaces the host gather
+ * `self.embeddings[i]` + re-encoding of reference sotasum/mips.py:428,465-470 when the memory encoder is
+ * frozen, so that the cosine doc score of retriever_generator.py:158-172 can be recomputed with gradient
+ * w.r.t. the query. ids outside [id_offset, id_offset + ntotal) (other shards, -1 padding) give zero
+ * rows: a row-sharded bank sums the ranks' outputs. Async on `stream`. */
+int mips_gather_rows(mips_handle h, const int64_t* ids, int64_t n, int64_t id_offset, float* out, void* stream);
+
+/* Pre-tokenised memory store [n_rows, L] int32 (+ token counts [n_rows]) in HBM -> the four tensors the
+ * reference builds per step by re-tokenising the retrieved texts on the host (sotasum/mips.py:473-501):
+ * input_ids, attention_mask (t < len), memory_attention_mask (attention_mask with bos/eos positions
+ * cleared; optional) and global_attention_mask (1 on the first token; optional), all int64 [n, L].
+ * ids < 0 or >= n_rows give pad rows with zero masks. All pointers device memory. Async on `stream`. */
+int mips_gather_tokens(const int32_t* store_ids, const int32_t* store_len, int64_t n_rows, int L, const int64_t* ids,
+                       int64_t n, int32_t pad_id, int32_t bos_id, int32_t eos_id, int64_t* input_ids,
+                       int64_t* attention_mask, int64_t* memory_attention_mask, int64_t* global_attention_mask,
+                       void* stream);
 
 #ifdef __cplusplus
 }

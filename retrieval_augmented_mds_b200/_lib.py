@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         "mips_destroy": (i32, [vp]),
         "mips_reset": (i32, [vp]),
         "mips_ntotal": (i64, [vp]),
+        "mips_capacity": (i64, [vp]),
         "mips_dim": (i32, [vp]),
         "mips_metric": (i32, [vp]),
         "mips_dtype": (i32, [vp]),
@@ -68,6 +69,8 @@ def lib() -> C.CDLL:
         "mips_launch_count": (i64, []),
         "mips_last_algo": (C.c_char_p, [vp]),
         "mips_fallback_queries": (i64, [vp, i32]),
+        "mips_gather_rows": (i32, [vp, vp, i64, i64, vp, vp]),
+        "mips_gather_tokens": (i32, [vp, vp, i64, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
         "mips_retriever_metrics": (i32, [vp, i32, i32, vp, i64, vp, vp, vp, vp, vp, vp]),
         "mips_set_profiling": (i32, [vp, i32]),
         "mips_k1_ms_total": (f32, [vp]),

@@ -21,6 +21,7 @@
 #include "k2_merge.cuh"
 #include "k3_rerank.cuh"
 #include "k4_metrics.cuh"
+#include "k5_gather.cuh"
 #include "mips_b200.h"
 
 // ------------------------------------------------------------------------------------------
@@ -332,6 +333,7 @@ int mips_reset(mips_handle h) {
 }
 
 int64_t mips_ntotal(mips_handle h) { return h ? h->ntotal : -1; }
+int64_t mips_capacity(mips_handle h) { return h ? h->capacity : -1; }
 int mips_dim(mips_handle h) { return h ? h->d : -1; }
 int mips_metric(mips_handle h) { return h ? h->metric : -1; }
 int mips_dtype(mips_handle h) { return h ? h->dtype : -1; }
@@ -977,6 +979,39 @@ int mips_retriever_metrics(const int64_t* ids, int nq, int k, const int64_t* row
   LAUNCH_CHECK("retrieval_metrics_rows_kernel");
   retrieval_metrics_mean_kernel<<<1, 256, 0, st>>>(per_query, nq, out3);
   LAUNCH_CHECK("retrieval_metrics_mean_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ gather
+int mips_gather_rows(mips_handle h, const int64_t* ids, int64_t n, int64_t id_offset, float* out, void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (n < 0 || (n > 0 && (!ids || !out))) return set_err(MIPS_E_INVALID, "bad ids / out");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((n + 7) / 8);
+  if (h->dtype == MIPS_DTYPE_BF16)
+    gather_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(h->bank), h->ntotal,
+                                                             h->d, h->d_pad, ids, n, id_offset, out);
+  else
+    gather_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(h->bank), h->ntotal, h->d, h->d_pad,
+                                                     ids, n, id_offset, out);
+  LAUNCH_CHECK("gather_rows_kernel");
+  return 0;
+}
+
+int mips_gather_tokens(const int32_t* store_ids, const int32_t* store_len, int64_t n_rows, int L, const int64_t* ids,
+                       int64_t n, int32_t pad_id, int32_t bos_id, int32_t eos_id, int64_t* input_ids,
+                       int64_t* attention_mask, int64_t* memory_attention_mask, int64_t* global_attention_mask,
+                       void* stream) {
+  if (n < 0 || L < 1 || n_rows < 0) return set_err(MIPS_E_INVALID, "bad n / L / n_rows");
+  if (n == 0) return 0;
+  if (!store_ids || !store_len || !ids || !input_ids || !attention_mask) return set_err(MIPS_E_INVALID, "null buffers");
+  if (n > 0x7fffffff) return set_err(MIPS_E_INVALID, "too many rows to gather in one call");
+  gather_tokens_kernel<<<static_cast<unsigned>(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      store_ids, store_len, n_rows, L, ids, pad_id, bos_id, eos_id, input_ids, attention_mask, memory_attention_mask,
+      global_attention_mask);
+  LAUNCH_CHECK("gather_tokens_kernel");
   return 0;
 }
 

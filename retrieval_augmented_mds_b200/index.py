@@ -80,6 +80,10 @@ class B200FlatIndex:
     def ntotal(self) -> int:
         return int(self._L.mips_ntotal(self._h))
 
+    @property
+    def capacity(self) -> int:
+        return int(self._L.mips_capacity(self._h))
+
     def reset(self) -> None:
         check(self._L.mips_reset(self._h))
 
@@ -137,6 +141,18 @@ class B200FlatIndex:
         out = np.empty((n, self.d), dtype=np.float32)
         check(self._L.mips_reconstruct(self._h, i0, n, out.ctypes.data_as(C.c_void_p), 0, self._stream()))
         return out
+
+    def gather_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """Stored rows by GLOBAL id, float32 [..., d] on the device: what the reference
+        re-encodes per step (mips.py:465-470) when the memory encoder is frozen. ids outside this
+        shard (other ranks' rows, -1 padding) give zero rows — sum the ranks' outputs for a sharded bank."""
+        if not ids.is_cuda or ids.dtype != torch.int64:
+            raise ValueError("gather_rows needs a CUDA int64 id tensor")
+        flat = ids.contiguous().view(-1)
+        out = torch.empty((flat.shape[0], self.d), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._L.mips_gather_rows(self._h, _ptr(flat), flat.shape[0], self.id_offset, _ptr(out), self._stream()))
+        return out.view(*ids.shape, self.d)
 
     # ------------------------------------------------------------------ search side
     def _check_k(self, k: int) -> int:
@@ -425,3 +441,49 @@ def retriever_metrics(ids: torch.Tensor, row_aid: torch.Tensor, query_aid: torch
     if return_pred:
         out["pred"] = pred
     return out
+
+
+class MemoryTokenStore:
+    """The memory's documents tokenised ONCE and kept in HBM ([N, L] int32 + token counts), gathered by the
+    search's ids on the device. Replaces the per-step host work of reference
+    sotasum/mips.py:428,473-501: Arrow text lookup of the retrieved rows, `memory_tokenizer(flat_texts,
+    padding="max_length", truncation=True)`, and the derived masks."""
+
+    def __init__(self, input_ids, lengths=None, attention_mask=None, pad_id: int = 1, bos_id: int = 0,
+                 eos_id: int = 2, device=None):
+        dev = torch.device("cuda", _device_index(device))
+        ids = torch.as_tensor(np.asarray(input_ids) if not isinstance(input_ids, torch.Tensor) else input_ids)
+        if ids.dim() != 2:
+            raise ValueError("input_ids must be [N, L]")
+        if lengths is None:
+            if attention_mask is None:
+                raise ValueError("pass lengths [N] or attention_mask [N, L]")
+            am = torch.as_tensor(np.asarray(attention_mask) if not isinstance(attention_mask, torch.Tensor) else attention_mask)
+            lengths = am.to(torch.int64).sum(1)         # right padding (padding="max_length"): a prefix of ones
+        self.input_ids = ids.to(dev, torch.int32).contiguous()
+        self.lengths = torch.as_tensor(lengths).to(dev, torch.int32).contiguous()
+        self.pad_id, self.bos_id, self.eos_id = int(pad_id), int(bos_id), int(eos_id)
+        self.device = dev
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.input_ids.shape[0])
+
+    @property
+    def seq_len(self) -> int:
+        return int(self.input_ids.shape[1])
+
+    def gather(self, ids: torch.Tensor) -> dict:
+        """ids int64 [B, k] (CUDA) -> memory_input_ids / attention_mask / memory_attention_mask /
+        global_attention_mask, int64 [B*k, L] like the tensors of mips.py:473-501."""
+        if not ids.is_cuda or ids.dtype != torch.int64:
+            raise ValueError("gather needs a CUDA int64 id tensor")
+        flat = ids.contiguous().view(-1)
+        n, L = flat.shape[0], self.seq_len
+        outs = [torch.empty((n, L), dtype=torch.int64, device=self.device) for _ in range(4)]
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            check(_lib.lib().mips_gather_tokens(_ptr(self.input_ids), _ptr(self.lengths), self.n_rows, L, _ptr(flat), n,
+                                                self.pad_id, self.bos_id, self.eos_id, *[_ptr(o) for o in outs], st))
+        return {"memory_input_ids": outs[0], "attention_mask": outs[1], "memory_attention_mask": outs[2],
+                "global_attention_mask": outs[3]}

@@ -94,6 +94,62 @@ class Mips:
         if isinstance(self.args.mips_nprobe, int):
             self.index.nprobe = self.args.mips_nprobe   # mips.py:342-345
 
+    # ------------------------------------------------------------------ refresh (lightning_model.py:148-180)
+    # The reference rebuilds its memory every `mips_rebuild_every` steps with three barriers, a disk
+    # round trip of the whole bank and a rank-0 faiss add while every other rank waits
+    # (_build_mips_index2). Here the bank is double buffered in HBM: the encoder's CLS
+    # rows (already on the GPU, mips.py:351-356) are ingested by K0 into the BACK shard on a side
+    # stream while searches keep hitting the FRONT shard; commit is two tiny collectives and a swap.
+    def needs_refresh(self, global_step: int, rebuild_every: int, frozen: bool = False) -> bool:
+        """The schedule of on_train_batch_start (lightning_model.py:148-163)."""
+        return (not frozen) and global_step % rebuild_every == 0 and global_step not in self.rebuilt_steps
+
+    def begin_refresh(self, n_rows_local: int, d: Optional[int] = None) -> None:
+        """Open the back buffer for `n_rows_local` rows of THIS rank (encode_text2's partition,
+        mips.py:226-230). The previous back buffer is reused when it is large enough (no cudaMalloc)."""
+        d = d if d is not None else self.index.d
+        back = getattr(self, "_back", None)
+        if back is not None and back.d == d and back.capacity >= n_rows_local and back.dtype == self.args.bank_dtype:
+            back.reset()
+        else:
+            back = B200FlatIndex(d, METRIC_INNER_PRODUCT, dtype=self.args.bank_dtype, device=self.device,
+                                 capacity=max(n_rows_local, 1))
+        self._back = back
+        if getattr(self, "_refresh_stream", None) is None:
+            self._refresh_stream = torch.cuda.Stream(device=back.device)
+        self._refresh_stream.wait_stream(torch.cuda.current_stream(back.device))
+
+    def refresh_add(self, embeddings: torch.Tensor) -> None:
+        """One block of freshly encoded rows (CUDA float tensor [n, d]) -> back shard, on the side stream."""
+        if self.args.mips_db_max_size is not None:
+            room = self.args.mips_db_max_size - self._back.ntotal
+            embeddings = embeddings[: max(room, 0)]
+            if embeddings.shape[0] == 0:
+                return
+        fuse_norm = bool(self.normalize and self.metric_type == METRIC_INNER_PRODUCT)
+        with torch.cuda.stream(self._refresh_stream):
+            self._back.add(embeddings, normalize=fuse_norm)
+
+    def commit_refresh(self, global_step: int) -> None:
+        """Make the back buffer the one searches see (collective when the bank is row-sharded)."""
+        back = self._back
+        torch.cuda.current_stream(back.device).wait_stream(self._refresh_stream)
+        front = self.index
+        self.index = back
+        if self.group is not None:
+            self._sharded = _sharded.ShardedFlatIndex(back, self.group)
+            off, self._sharded.counts = _sharded.exchange_offsets(back.ntotal, self.group, back.device)
+            back.id_offset = off
+            mn2 = _sharded.allreduce_max(back.max_norm2(), self.group, back.device)
+        else:
+            mn2 = back.max_norm2()
+        self.max_norm = float(np.sqrt(mn2))
+        if self.metric_type == METRIC_L2:
+            self.phi = mn2
+            back.phi = mn2
+        self._back = front                          # next refresh ingests into the old front
+        self.rebuilt_steps.append(global_step)      # lightning_model.py:179
+
     # ------------------------------------------------------------------ query prep (mips.py:368-375)
     def l2_normalization(self, x: np.ndarray) -> np.ndarray:
         if not x.flags.c_contiguous:

@@ -139,3 +139,89 @@ def test_retriever_metrics_edge_cases(cuda_device):
     wb = o.retriever_metrics(rb["pred"].cpu().numpy(), np.full(5, 3.0, np.float32))
     for key in wb:
         assert np.isclose(rb[key], wb[key], rtol=1e-6, atol=1e-7), key
+
+
+# ----------------------------------------------------------------------------------------- N2
+def test_gather_tokens_matches_host_tokenisation(cuda_device):
+    """The four tensors of mips.py:473-501 from a pre-tokenised HBM store == numpy indexing + the
+    reference's mask statements (restated below), incl. -1 ids."""
+    rng = np.random.default_rng(4)
+    N, L, pad, bos, eos = 300, 48, 1, 0, 2
+    lens = rng.integers(3, L + 1, N)
+    store = np.full((N, L), pad, np.int32)
+    for i, n in enumerate(lens):
+        store[i, :n] = rng.integers(3, 5000, n)
+        store[i, 0], store[i, n - 1] = bos, eos
+    att = (np.arange(L)[None, :] < lens[:, None]).astype(np.int64)
+    ms = pkg.MemoryTokenStore(store, attention_mask=att, pad_id=pad, bos_id=bos, eos_id=eos)
+    ids = rng.integers(0, N, (7, 5)).astype(np.int64)
+    ids[2, 3:] = -1
+    out = {k: v.cpu().numpy() for k, v in ms.gather(torch.from_numpy(ids).cuda()).items()}
+    flat = ids.reshape(-1)
+    ok = flat >= 0
+    want_ids = np.where(ok[:, None], store[np.maximum(flat, 0)], pad).astype(np.int64)
+    want_att = np.where(ok[:, None], att[np.maximum(flat, 0)], 0)
+    want_mem = np.where((want_ids == eos) | (want_ids == bos), 0, want_att)          # mips.py:494-501
+    want_glob = np.zeros_like(want_ids)
+    want_glob[:, 0] = 1                                                               # mips.py:483-487
+    assert np.array_equal(out["memory_input_ids"], want_ids)
+    assert np.array_equal(out["attention_mask"], want_att)
+    assert np.array_equal(out["memory_attention_mask"], want_mem)
+    assert np.array_equal(out["global_attention_mask"], want_glob)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_gather_rows_gives_differentiable_doc_scores(cuda_device, dtype):
+    """Bank rows gathered by the search's ids reproduce the merge kernel's cosine doc scores
+    (retriever_generator.py:158-172) and let the gradient reach the query."""
+    xb, xq = _data(5000, 96, 6, 8)
+    idx = pkg.B200FlatIndex(96, 0, dtype=dtype)
+    idx.add(xb)
+    q = torch.from_numpy(xq).cuda()
+    r = idx.search_ex(q, 5, want=("scores", "ids", "cosine"))
+    rows = idx.gather_rows(r["ids"])                                  # [6, 5, 96] fp32, no host round trip
+    stored = xb if dtype == "fp32" else o.bf16_round(xb)
+    assert np.array_equal(rows.cpu().numpy(), stored[r["ids"].cpu().numpy()])
+    qg = (q if dtype == "fp32" else q.bfloat16().float()).clone().requires_grad_(True)
+    cos = torch.nn.functional.cosine_similarity(qg[:, None, :], rows, dim=-1)
+    torch.testing.assert_close(cos, r["cosine"], rtol=1e-4, atol=1e-5)
+    cos.sum().backward()
+    assert qg.grad is not None and bool(torch.isfinite(qg.grad).all()) and float(qg.grad.abs().sum()) > 0
+    none = idx.gather_rows(torch.tensor([[-1, 10**9]], dtype=torch.int64).cuda())
+    assert float(none.abs().sum()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------- N1
+def test_double_buffered_refresh_serves_old_bank_until_commit(cuda_device):
+    """Memory refresh on the device (lightning_model.py:148-180 without barriers or disk): searches
+    keep seeing the old bank while the new one is ingested on a side stream; commit swaps."""
+    xa, xq = _data(6000, 64, 10, 21)
+    xb, _ = _data(5000, 64, 1, 22)
+    cfg = pkg.MipsConfig(mips_metric_type=0, mips_normalize=True, bank_dtype="fp32")
+    mips = pkg.Mips(cfg)
+    mips.build_index(xa)
+    xq = mips._prepare_query(xq)                                  # Mips.search takes prepared queries (mips.py:368-375)
+    assert mips.needs_refresh(0, 100) is False and mips.needs_refresh(100, 100) and not mips.needs_refresh(150, 100)
+    assert not mips.needs_refresh(100, 100, frozen=True)
+    s_old, i_old = mips.search(xq, None, 5)
+    mips.begin_refresh(5000)
+    tb = torch.from_numpy(xb).cuda()
+    for s in range(0, 5000, 1000):
+        mips.refresh_add(tb[s:s + 1000])                          # side stream
+        s_mid, i_mid = mips.search(xq, None, 5)                   # front bank, default stream
+        assert np.array_equal(np.asarray(i_mid), np.asarray(i_old))
+    mips.commit_refresh(100)
+    assert mips.rebuilt_steps == [0, 100] and mips.index.ntotal == 5000
+    s_new, i_new = mips.search(xq, None, 5)
+    D_ref, I_ref = o.exact_topk_f64(o.normalize_L2(xb), xq, 5)
+    o.check_topk(o.normalize_L2(xb), xq, np.asarray(s_new), np.asarray(i_new), 0, rtol=1e-5,
+                 D_ref=D_ref, I_ref=I_ref, what="after refresh")
+    assert np.isclose(mips.max_norm, np.sqrt(o.get_phi(xb)), rtol=1e-5)
+    # the old front is the next back buffer: a second refresh reuses its allocation
+    back_before = mips._back
+    mips.begin_refresh(6000)
+    assert mips._back is back_before and mips._back.ntotal == 0
+    mips.refresh_add(torch.from_numpy(xa).cuda())
+    mips.commit_refresh(200)
+    s2, i2 = mips.search(xq, None, 5)
+    assert np.array_equal(np.asarray(i2), np.asarray(i_old))
