@@ -55,7 +55,11 @@ __device__ __noinline__ float topk_list_insert(float* keys, int* ids, int k, flo
 // ---------------------------------------------------------------------------------------------
 // Per-thread top-k SETS (CTA-pair kernel, thread <-> query epilogue).
 // Each query owns an UNSORTED set of KCAP >= k (ordered key, id) pairs in shared memory with the
-// slot of its WORST entry tracked in a register; K2 merges sets by arg-max rounds and does not
+// slot of its WORST entry tracked in a register. The 32 sets of a warp are INTERLEAVED: key i of
+// lane t sits at warp_base[i * 32 + t] (ids follow the KCAP * 32 keys), so lanes that touch the same entry index together (the
+// common case while many queries still admit candidates) hit 32 different banks; a per-lane
+// contiguous layout made every such access a 32-way bank conflict (~2300 cycles per admission at
+// k = 32, ncu: 43 % short-scoreboard stalls inside topk_replace). K2 merges sets by arg-max rounds and does not
 // need them sorted. Keys are order-preserving uint32 images of the fp32 score; unused slots
 // [k, KCAP) hold the never-worst sentinel 0xffffffff and are skipped on output.
 __device__ __forceinline__ uint32_t f32_to_ordered(float f) {
@@ -67,48 +71,80 @@ __device__ __forceinline__ float ordered_to_f32(uint32_t u) {
 }
 __host__ __device__ inline int topk_kcap(int k) { return k <= 8 ? 8 : k <= 16 ? 16 : k <= 32 ? 32 : 64; }
 
-// Admission: store (sk, id) into the worst slot, then find the new worst entry = the minimum of
-// the composite (key, ~id), i.e. the lowest key and among equal keys the highest id (the last in
-// the (key desc, id asc) order; empty slots carry id 0xffffffff). Straight-line code: the loads
-// of a 16-entry chunk are issued back to back and reduced by a tournament, so an admission costs
-// ~100 cycles per chunk; the sorted insert / dynamic rescan loops it replaces measured 800-1600
-// cycles at k = 32 (ncu source page: ~50 cycles per entry of dependent load-compare-select).
+// Admission: store (sk, id) into the worst slot, then find the new worst entry: the lowest key and,
+// among equal keys, the highest id (the last in the (key desc, id asc) order; empty slots carry id
+// 0xffffffff). Keys and ids are separate arrays (`ids = keys + KCAP * 32`), so the common case only
+// touches keys: the loads of a 32-key chunk are issued back to back, one integer min per tree node
+// finds the lowest key, one compare per key marks where it sits; ids are read only to break an
+// exact tie. ~130 instructions at k = 32 where a tournament on the 64-bit composite (key, ~id) took
+// ~300 (~1000 cycles per admission, ncu) and the sorted insert / dynamic rescan loops before it
+// measured ~50 cycles per entry of dependent load-compare-select.
+constexpr int TOPK_STRIDE = 32;   // lanes of a warp interleave their sets entry by entry
 template <int KCAP>
-__device__ __forceinline__ uint2 topk_replace_fixed(uint2* set, int worst, uint32_t sk, int id) {
-  set[worst] = make_uint2(sk, static_cast<uint32_t>(id));
-  constexpr int CH = KCAP < 16 ? KCAP : 16;
-  unsigned long long best = ~0ull;
-  int best_pos = 0;
+__device__ __forceinline__ uint2 topk_replace_fixed(uint32_t* keys, int worst, uint32_t sk, int id) {
+  uint32_t* ids = keys + KCAP * TOPK_STRIDE;
+  keys[worst * TOPK_STRIDE] = sk;
+  ids[worst * TOPK_STRIDE] = static_cast<uint32_t>(id);
+  constexpr int CH = KCAP < 32 ? KCAP : 32;
+  constexpr int NCH = KCAP / CH;
+  uint32_t m = 0xffffffffu;
+  uint32_t eq[NCH];
 #pragma unroll
-  for (int base = 0; base < KCAP; base += CH) {
-    unsigned long long c[CH];
-    int p[CH];
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t kk[CH], t[CH];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const uint2 e = set[base + i];
-      c[i] = (static_cast<unsigned long long>(e.x) << 32) | static_cast<uint32_t>(~e.y);
-      p[i] = base + i;
-    }
+    for (int i = 0; i < CH; ++i) t[i] = kk[i] = keys[(c * CH + i) * TOPK_STRIDE];
 #pragma unroll
-    for (int w = 1; w < CH; w <<= 1) {
+    for (int w = 1; w < CH; w <<= 1)
 #pragma unroll
-      for (int i = 0; i + w < CH; i += 2 * w) {
-        const bool lt = c[i + w] < c[i];
-        c[i] = lt ? c[i + w] : c[i];
-        p[i] = lt ? p[i + w] : p[i];
-      }
-    }
-    if (c[0] < best) {
-      best = c[0];
-      best_pos = p[0];
+      for (int i = 0; i + w < CH; i += 2 * w) t[i] = min(t[i], t[i + w]);
+    const uint32_t mc = t[0];
+    uint32_t e = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) e |= (kk[i] == mc ? 1u : 0u) << i;
+    eq[c] = e;
+    if (c == 0) {
+      m = mc;
+    } else if (mc < m) {      // a later chunk holds a lower key: earlier marks are void
+      m = mc;
+#pragma unroll
+      for (int j = 0; j < c; ++j) eq[j] = 0;
+    } else if (mc > m) {
+      eq[c] = 0;
     }
   }
-  return make_uint2(static_cast<uint32_t>(best >> 32), static_cast<uint32_t>(best_pos));
+  int pos = -1;
+  uint32_t best_id = 0;
+  bool tie = false;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (eq[c]) {
+      tie = tie || pos >= 0 || (eq[c] & (eq[c] - 1)) != 0;
+      if (pos < 0) pos = c * CH + __ffs(eq[c]) - 1;
+    }
+  }
+  if (tie) {   // rare: several entries share the lowest key, evict the one with the highest id
+    pos = -1;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t e = eq[c];
+      while (e) {
+        const int i = c * CH + __ffs(e) - 1;
+        e &= e - 1;
+        const uint32_t v = ids[i * TOPK_STRIDE];
+        if (pos < 0 || v > best_id) {
+          best_id = v;
+          pos = i;
+        }
+      }
+    }
+  }
+  return make_uint2(m, static_cast<uint32_t>(pos));
 }
 // returns (worst key after the admission = new threshold, its slot)
-__device__ __noinline__ uint2 topk_replace(uint2* set, int kcap, int worst, uint32_t sk, int id) {
-  if (kcap == 8) return topk_replace_fixed<8>(set, worst, sk, id);
-  if (kcap == 16) return topk_replace_fixed<16>(set, worst, sk, id);
-  if (kcap == 32) return topk_replace_fixed<32>(set, worst, sk, id);
-  return topk_replace_fixed<64>(set, worst, sk, id);
+__device__ __noinline__ uint2 topk_replace(uint32_t* keys, int kcap, int worst, uint32_t sk, int id) {
+  if (kcap == 8) return topk_replace_fixed<8>(keys, worst, sk, id);
+  if (kcap == 16) return topk_replace_fixed<16>(keys, worst, sk, id);
+  if (kcap == 32) return topk_replace_fixed<32>(keys, worst, sk, id);
+  return topk_replace_fixed<64>(keys, worst, sk, id);
 }

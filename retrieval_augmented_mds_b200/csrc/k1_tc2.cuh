@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t pick128(const uint32_t (&v)[4][32], int c) {
 // the admission threshold; the set is only touched when a score beats it.
 template <bool kL2>
 __device__ __forceinline__ void fold_tile(uint32_t (&v)[4][32], const float* xnorm2, int id0,
-                                          int64_t ntotal, int ign, bool live, uint2* set, int kcap,
+                                          int64_t ntotal, int ign, bool live, uint32_t* set, int kcap,
                                           float& thr, int& worst) {
   if (kL2) {
     // ranking key for L2: <q,x> - |x|^2/2 (same address for every lane: broadcast loads)
@@ -169,7 +169,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
   const uint32_t a_off = 0;
   const uint32_t st_off = static_cast<uint32_t>(n_akch) * ABOX_BYTES;
   const uint32_t lists_off = st_off + static_cast<uint32_t>(S) * STAGE_BYTES;
-  uint2* lists = reinterpret_cast<uint2*>(gen + lists_off);   // [128 queries][kcap] (ordered key, id)
+  uint32_t* lists = reinterpret_cast<uint32_t*>(gen + lists_off);   // per warp: keys [kcap][32], ids [kcap][32]
   const uint32_t bars_off = lists_off + list_bytes(p.k);
   const uint32_t bars = base + bars_off;
   auto full_bar = [&](int i) { return bars + 8u * i; };                       // leader's is used
@@ -381,9 +381,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
     }
 
     const int kcap = topk_kcap(p.k);
-    uint2* set = lists + row * kcap;
-    for (int i = 0; i < kcap; ++i)
-      set[i] = i < p.k ? make_uint2(f32_to_ordered(-CUDART_INF_F), 0xffffffffu) : make_uint2(0xffffffffu, 0u);
+    uint32_t* set = lists + warp * 64 * kcap + lane;   // this query's keys: key i at set[i * 32], id i at set[(kcap + i) * 32]
+    for (int i = 0; i < kcap; ++i) {
+      set[i * TOPK_STRIDE] = i < p.k ? f32_to_ordered(-CUDART_INF_F) : 0xffffffffu;   // [k, kcap): never the worst
+      set[(kcap + i) * TOPK_STRIDE] = 0xffffffffu;
+    }
     int worst = 0;
     float thr = -CUDART_INF_F;
     const bool live = qrow < p.nq;
@@ -413,9 +415,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
     if (live) {
       const size_t o = (static_cast<size_t>(split) * p.nq + qrow) * p.k;
       for (int i = 0; i < p.k; ++i) {   // unsorted: K2 merges by arg-max rounds
-        const uint2 e = set[i];
-        p.part_key[o + i] = ordered_to_f32(e.x);
-        p.part_ids[o + i] = static_cast<int>(e.y);
+        p.part_key[o + i] = ordered_to_f32(set[i * TOPK_STRIDE]);
+        p.part_ids[o + i] = static_cast<int>(set[(kcap + i) * TOPK_STRIDE]);
       }
     }
   }
