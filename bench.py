@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -215,15 +215,17 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
 
     # ---- device-resident timing
+    # clocks / throttle reasons are sampled under load from the warm-up to the end of the e2e loop: at
+    # N=8 the K timed steps alone can be shorter than one nvidia-smi sampling period
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     barrier()
     idx.set_profiling(True)
     L = _lib.lib()
     launches0 = L.mips_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -234,7 +236,6 @@ def run_ours(args) -> None:
     launches = L.mips_launch_count() - launches0
     k1_ms, k1_n = idx.k1_ms_total()
     idx.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
     barrier()
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -253,6 +254,13 @@ def run_ours(args) -> None:
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_ms_step = 1e3 * float(e2e_s.item()) / args.steps
+    if rank == 0 and len(sampler.rows) < 3:      # very short runs: keep the GPU under load until a few samples exist
+        t_end = time.perf_counter() + 1.0
+        while len(sampler.rows) < 3 and time.perf_counter() < t_end:
+            idx.search_ex(xq_dev, k, algo=args.algo)
+            torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    barrier()
 
     # sanity: the timed path returns a real result (ids valid, scores descending)
     ids = out["ids"]
