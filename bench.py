@@ -175,6 +175,43 @@ def run_ours(args) -> None:
 
     n, d, nq, k = args.rows, DIM, args.nq, args.k
     rows = balanced_range(n, rank, world)
+    shard_policy = "equal"
+    if world > 1 and args.balance == "calibrated":
+        # Strong scaling waits for the slowest shard every step and the boards of one box differ by
+        # several percent under the 1 kW cap: size the shards by each GPU's measured search throughput
+        # (a ~1.5 s sustained probe of the same kernel on a small synthetic bank), clamped to +-10 %.
+        from retrieval_augmented_mds_b200.sharded import weighted_ranges
+        probe_rows = 500_000
+        pidx = m.B200FlatIndex(d, m.METRIC_INNER_PRODUCT, dtype="bf16", device=dev, capacity=probe_rows)
+        pgen = torch.Generator(device=dev).manual_seed(7)
+        pidx.add(torch.randn((probe_rows, d), generator=pgen, device=dev))
+        pq = torch.randn((nq, d), generator=pgen, device=dev)
+        for _ in range(50):
+            pidx.search_ex(pq, k, algo=args.algo)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        reps = 0
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        while time.perf_counter() - t0 < 1.5:
+            if reps == 600:                      # time the tail: clocks have settled under the power cap
+                pe0.record()
+            pidx.search_ex(pq, k, algo=args.algo)
+            reps += 1
+            if reps % 100 == 0:
+                torch.cuda.synchronize()
+        pe1.record()
+        torch.cuda.synchronize()
+        speed = (reps - 600) / pe0.elapsed_time(pe1) if reps > 700 else 1.0
+        sp = torch.tensor([speed], dtype=torch.float64, device=dev)
+        allsp = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allsp, sp)
+        weights = allsp.cpu().tolist()
+        rows = weighted_ranges(n, weights)[rank]
+        shard_policy = "calibrated: rows proportional to measured per-GPU search throughput " + \
+                       "[" + ", ".join(f"{w / (sum(weights) / world):.3f}" for w in weights) + "]"
+        pidx.close()
+        del pidx
     idx = m.B200FlatIndex(d, m.METRIC_INNER_PRODUCT, dtype="bf16", device=dev, capacity=len(rows),
                           id_offset=rows.start)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -188,9 +225,12 @@ def run_ours(args) -> None:
     qgen = torch.Generator(device="cpu").manual_seed(4321)       # identical queries on every rank
     xq_host = torch.randn((nq, d), generator=qgen, dtype=torch.float32).pin_memory()
     xq_dev = xq_host.to(dev)
-    sh = ShardedFlatIndex(idx) if world > 1 else None
+    sh = ShardedFlatIndex(idx, exchange=args.exchange) if world > 1 else None
     if sh is not None:
-        sh.counts = [len(balanced_range(n, r, world)) for r in range(world)]
+        cnt = torch.tensor([len(rows)], dtype=torch.int64, device=dev)
+        allc = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt)
+        sh.counts = [int(c) for c in allc.cpu().tolist()]
 
     def step_device():
         if sh is not None:
@@ -288,7 +328,8 @@ def run_ours(args) -> None:
                                    f"k={k}, exact inner-product search (BASELINE config 3)",
                        "rows_per_gpu": len(rows), "l2_policy": "inputs larger than L2 (bank shard "
                                    f"{len(rows) * d * 2 / 1e9:.2f} GB per GPU vs 126 MB L2)",
-                       "search_kernel": idx.last_algo, "bank_build_s": round(build_s, 3)},
+                       "search_kernel": idx.last_algo, "bank_build_s": round(build_s, 3),
+                       "exchange": (sh.exchange if sh is not None else "none"), "shards": shard_policy},
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic,
                          "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a multi-step loop)",
@@ -302,6 +343,8 @@ def run_ours(args) -> None:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_reference_leg(nq, d, k, n)
         print(json.dumps(line))
+    if sh is not None:
+        sh.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -316,6 +359,11 @@ def main() -> None:
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--algo", default="auto", choices=["auto", "tc", "tc128", "tc2", "tcx", "simt"], help="K1 variant (A/B runs)")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"],
+                    help="cross-GPU step: NCCL all-gather or peer-memory exchange fused into the merge kernels "
+                         "(default: MIPS_B200_EXCHANGE or the library default)")
+    ap.add_argument("--balance", default="equal", choices=["equal", "calibrated"],
+                    help="N>1: equal row shards, or shards proportional to each GPU's measured search throughput")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -207,6 +207,33 @@ int mips_gather_tokens(const int32_t* store_ids, const int32_t* store_len, int64
                        int64_t* attention_mask, int64_t* memory_attention_mask, int64_t* global_attention_mask,
                        void* stream);
 
+/* ---- peer-memory exchange of the per-rank lists (multi-GPU, one box) ------------------------ */
+
+/* The cross-GPU step of the sharded search (absent in the reference, which never shards) without a
+ * collective launch: every rank owns an exchange buffer that its peers map through CUDA IPC; the local
+ * merge kernel of rank r stores its [nq, k] 16-byte records into slot r of EVERY rank's buffer over
+ * NVLink and raises rank r's flag there; the final merge kernel of each rank waits for the G flags of
+ * this search (`seq`) and merges its own buffer. Callers alternate two slot sets between consecutive
+ * searches (a rank may be one search ahead of a peer).
+ *   mips_xchg_alloc : cudaMalloc + zero + IPC handle (64 bytes) of a buffer on `device`
+ *   mips_xchg_open  : map a peer's buffer from its handle; mips_xchg_close / mips_xchg_free undo them
+ *   mips_search_local_xchg : mips_search_local_packed whose output goes to peer_bufs[g] (device array of
+ *       n_peers pointers to this rank's [nq, k] region on each rank, itself included) and whose
+ *       completion is signalled on peer_flags[g]; bf16 / SIMT single-chunk searches only
+ *   mips_merge_xchg : mips_merge_packed over my_buf = [n_ranks, nq, k_in] records once my_flags[0..n_ranks)
+ *       all read `seq` (bounded wait, then the kernel traps) */
+int mips_xchg_alloc(int device, int64_t bytes, void** ptr, void* handle64);
+int mips_xchg_open(int device, const void* handle64, void** ptr);
+int mips_xchg_close(int device, void* ptr);
+int mips_xchg_free(int device, void* ptr);
+int mips_search_local_xchg(mips_handle h, const float* q, int nq, int k, int q_normalize, const int64_t* ignore_ids,
+                           int64_t id_offset, int algo, void* const* peer_bufs, uint32_t* const* peer_flags,
+                           int n_peers, uint32_t seq, float* out_qnorm2, void* stream);
+int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, uint32_t seq, int nq, int k_in, int k_out,
+                    int metric, int out_mode, float phi, const float* q_norm2, const int64_t* ignore_ids, float* D,
+                    int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias, float* memory_bias,
+                    int mem_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

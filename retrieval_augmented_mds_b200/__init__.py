@@ -5,7 +5,7 @@ from .index import (METRIC_INNER_PRODUCT, METRIC_L2, B200FlatIndex, MemoryTokenS
                     index_factory, merge_candidates, normalize_L2, retriever_metrics)
 from .faiss_io import read_index, write_index
 from .mips import Mips, MipsConfig
-from .sharded import ShardedFlatIndex, balanced_range, shard_range
+from .sharded import ShardedFlatIndex, balanced_range, shard_range, weighted_ranges
 
 
 
@@ -29,4 +29,4 @@ def install_faiss_shim() -> str:
 
 __all__ = ["MemoryTokenStore", "retriever_metrics", "read_index", "write_index", "install_faiss_shim", "B200FlatIndex", "IndexFlat", "IndexFlatIP", "IndexFlatL2", "index_factory", "normalize_L2",
            "merge_candidates", "METRIC_INNER_PRODUCT", "METRIC_L2", "Mips", "MipsConfig",
-           "ShardedFlatIndex", "shard_range", "balanced_range"]
+           "ShardedFlatIndex", "shard_range", "balanced_range", "weighted_ranges"]

@@ -69,6 +69,13 @@ def lib() -> C.CDLL:
         "mips_launch_count": (i64, []),
         "mips_last_algo": (C.c_char_p, [vp]),
         "mips_fallback_queries": (i64, [vp, i32]),
+        "mips_xchg_alloc": (i32, [i32, i64, C.POINTER(vp), vp]),
+        "mips_xchg_open": (i32, [i32, vp, C.POINTER(vp)]),
+        "mips_xchg_close": (i32, [i32, vp]),
+        "mips_xchg_free": (i32, [i32, vp]),
+        "mips_search_local_xchg": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, i32, C.c_uint32, vp, vp]),
+        "mips_merge_xchg": (i32, [vp, vp, i32, C.c_uint32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, f32,
+                                  f32, vp, i32, vp]),
         "mips_gather_rows": (i32, [vp, vp, i64, i64, vp, vp]),
         "mips_gather_tokens": (i32, [vp, vp, i64, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
         "mips_retriever_metrics": (i32, [vp, i32, i32, vp, i64, vp, vp, vp, vp, vp, vp]),

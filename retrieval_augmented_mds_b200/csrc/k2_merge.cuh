@@ -22,6 +22,33 @@ struct __align__(16) PackedCand {
   int64_t id;
 };
 
+// Peer-memory exchange fused into the merge kernels (one box, NVLink/NVSwitch, CUDA IPC mappings):
+// the LOCAL merge of rank r stores its [nq, k] records straight into slot r of EVERY rank's exchange
+// buffer and the last warp to finish raises rank r's arrival flag on every rank; the FINAL merge of
+// each rank waits for the G flags of this search (`seq`) and merges what landed in its own buffer.
+// No collective launch, no host involvement; the only traffic is 16 * nq * k bytes per peer.
+struct XchgOut {
+  PackedCand* const* bufs;   // device array [n_peers]: this rank's region on every rank (itself included)
+  uint32_t* const* flags;    // device array [n_peers]: this rank's arrival flag on every rank
+  unsigned int* done;        // local counter of finished queries (returns to 0 at the end of the launch)
+  uint32_t seq;
+  int n_peers;               // 0: no exchange
+};
+struct XchgIn {
+  const uint32_t* flags;     // [n_ranks] arrival flags in THIS rank's buffer
+  uint32_t seq;
+  int n_ranks;               // 0: no exchange
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct MergeBest {
   float key;
   int64_t id;
@@ -45,7 +72,9 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     const PackedCand* __restrict__ cand_packed,   // !LOCAL: packed input instead of the 3 arrays
     PackedCand* __restrict__ out_packed,          // LOCAL: packed output instead of the 3 arrays
     const int* __restrict__ q_active = nullptr,   // only these queries are merged (others keep their outputs)
-    int stage_cap = 0) {                          // LOCAL: shared-memory staging entries per warp (dynamic smem)
+    int stage_cap = 0,                            // LOCAL: shared-memory staging entries per warp (dynamic smem)
+    XchgOut xo = XchgOut{nullptr, nullptr, nullptr, 0u, 0},   // LOCAL: publish to the peers
+    XchgIn xi = XchgIn{nullptr, 0u, 0}) {                     // FINAL: wait for the peers
   __shared__ float s_key[4][MIPS_MAX_K];
   __shared__ float s_xn2[4][MIPS_MAX_K];
   __shared__ float s_cos[4][MIPS_MAX_K];
@@ -53,6 +82,18 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
   const int q = blockIdx.x * 4 + w;
   if (q >= nq) return;
   if (q_active && !q_active[q]) return;
+  if (!LOCAL && xi.n_ranks > 0) {
+    // every rank's list of this search has landed in this rank's buffer (bounded wait: a missing peer
+    // is a launch failure, not a hang)
+    if (lane < xi.n_ranks) {
+      unsigned long long spins = 0;
+      while (ld_acquire_sys(xi.flags + lane) != xi.seq) {
+        __nanosleep(64);
+        if (++spins > (1ull << 27)) __trap();
+      }
+    }
+    __syncwarp();
+  }
 
   const int32_t* ids32 = static_cast<const int32_t*>(cand_ids_v);
   const int64_t* ids64 = static_cast<const int64_t*>(cand_ids_v);
@@ -139,8 +180,14 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
       }
       s_key[w][j] = b.key;
       s_xn2[w][j] = xn;
-      if (LOCAL && out_packed) out_packed[static_cast<size_t>(q) * k_out + j] = PackedCand{b.key, xn, b.id};
-      else out_ids[static_cast<size_t>(q) * k_out + j] = b.id;
+      if (LOCAL && xo.n_peers > 0) {
+        const PackedCand rec{b.key, xn, b.id};
+        for (int g = 0; g < xo.n_peers; ++g) xo.bufs[g][static_cast<size_t>(q) * k_out + j] = rec;
+      } else if (LOCAL && out_packed) {
+        out_packed[static_cast<size_t>(q) * k_out + j] = PackedCand{b.key, xn, b.id};
+      } else {
+        out_ids[static_cast<size_t>(q) * k_out + j] = b.id;
+      }
     }
   }
   __syncwarp();
@@ -150,6 +197,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
   for (int j = lane; j < k_out; j += 32) {
     const size_t o = static_cast<size_t>(q) * k_out + j;
     if (j >= n_found) {
+      if (LOCAL && xo.n_peers > 0) {
+        for (int g = 0; g < xo.n_peers; ++g) xo.bufs[g][o] = PackedCand{-CUDART_INF_F, 0.f, -1};
+        continue;
+      }
       if (LOCAL && out_packed) {
         out_packed[o] = PackedCand{-CUDART_INF_F, 0.f, -1};
         continue;
@@ -167,7 +218,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     }
     const float key = s_key[w][j], xn = s_xn2[w][j];
     if (LOCAL) {
-      if (!out_packed) {
+      if (!out_packed && xo.n_peers == 0) {
         out_key[o] = key;
         if (out_xn2) out_xn2[o] = xn;
       }
@@ -191,7 +242,22 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     s_cos[w][j] = cs;
     lmax = fmaxf(lmax, beta * cs + beta_bias);
   }
-  if (LOCAL) return;
+  if (LOCAL) {
+    if (xo.n_peers > 0) {
+      // this query's records are on their way to every peer; the last query to get here raises the flags
+      __syncwarp();
+      __threadfence_system();
+      if (lane == 0) {
+        const unsigned int ticket = atomicAdd(xo.done, 1u);
+        if (ticket == static_cast<unsigned int>(nq) - 1u) {
+          __threadfence_system();
+          *xo.done = 0u;
+          for (int g = 0; g < xo.n_peers; ++g) st_release_sys(xo.flags[g], xo.seq);
+        }
+      }
+    }
+    return;
+  }
   __syncwarp();
 
   if (doc_prob) {

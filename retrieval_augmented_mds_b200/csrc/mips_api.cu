@@ -60,7 +60,8 @@ struct mips_index_s {
   void* bank = nullptr;
   float* norm2 = nullptr;
   unsigned int* max_norm2_bits = nullptr;  // device scalars: [0] max |x|^2 of the RAW rows (get_phi),
-                                           // [1] max |x|^2 of the STORED rows, [2] max |x - bf16(x)|^2
+                                           // [1] max |x|^2 of the STORED rows, [2] max |x - bf16(x)|^2,
+                                           // [3] certificate fallback counter, [4] exchange completion counter
   // fp32 index only: bf16 shadow of the rows (tensor-core filter of the exact search, k3_rerank.cuh)
   __nv_bfloat16* shadow = nullptr;
   CUtensorMap tmap_shadow64;
@@ -289,8 +290,8 @@ int mips_create(mips_handle* out, int d, int metric, int dtype, int device, int6
   h->dtype = dtype;
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->max_norm2_bits), 4 * sizeof(unsigned int));
-  if (e == cudaSuccess) e = cudaMemset(h->max_norm2_bits, 0, 4 * sizeof(unsigned int));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->max_norm2_bits), 8 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->max_norm2_bits, 0, 8 * sizeof(unsigned int));
   h->fb_count_dev = reinterpret_cast<int*>(h->max_norm2_bits + 3);
   if (e != cudaSuccess) {
     delete h;
@@ -328,7 +329,7 @@ int mips_reset(mips_handle h) {
   CUDA_TRY(cudaSetDevice(h->device));
   h->ntotal = 0;
   h->phi = 0.f;
-  CUDA_TRY(cudaMemset(h->max_norm2_bits, 0, 4 * sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(h->max_norm2_bits, 0, 8 * sizeof(unsigned int)));
   return 0;
 }
 
@@ -642,7 +643,7 @@ static int launch_simt(mips_index_s* h, int nq, int k, const int* ign_local, boo
 static int launch_merge_local(mips_index_s* h, const float* part_key, const int* part_ids, const float* bank_xn2,
                               int n_parts, int nq, int k_in, int k_out, int64_t id_offset, float* out_key,
                               int64_t* out_ids, float* out_xn2, void* out_packed, const int* q_active,
-                              cudaStream_t st, const char* what) {
+                              cudaStream_t st, const char* what, const XchgOut* xo = nullptr) {
   const int C = n_parts * k_in;
   int cap = 0;
   if (C > 64 && C <= 6144) cap = C;
@@ -650,7 +651,7 @@ static int launch_merge_local(mips_index_s* h, const float* part_key, const int*
   merge_topk_kernel<true><<<(nq + 3) / 4, 128, smem, st>>>(
       part_key, part_ids, nullptr, bank_xn2, n_parts, nq, k_in, k_out, id_offset, nullptr, h->metric, MIPS_OUT_IP,
       0.f, nullptr, out_key, out_ids, out_xn2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
-      static_cast<PackedCand*>(out_packed), q_active, cap);
+      static_cast<PackedCand*>(out_packed), q_active, cap, xo ? *xo : XchgOut{nullptr, nullptr, nullptr, 0u, 0});
   LAUNCH_CHECK(what);
   return 0;
 }
@@ -665,7 +666,7 @@ static int tcx_split_list(int k) { return std::max(k, 16); }
 static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_normalize,
                         const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
                         int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
-                        cudaStream_t st) {
+                        cudaStream_t st, const XchgOut* xo = nullptr) {
   int rc;
   const size_t eb = elem_bytes(h);
   const int nq_pad = round_up_i(nq, (algo == MIPS_ALGO_TC2 || algo == MIPS_ALGO_TCX) ? tc2::PAIR_M : tc::BLOCK_M);
@@ -805,7 +806,7 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
 
   // local k-way merge: split lists -> one list per query, global ids, |x|^2 gathered
   rc = launch_merge_local(h, h->part_key, h->part_ids, h->norm2, n_parts, nq, k, k, id_offset, out_key, out_ids,
-                          out_xnorm2, out_packed, nullptr, st, "merge_topk_kernel<local>");
+                          out_xnorm2, out_packed, nullptr, st, "merge_topk_kernel<local>", xo);
   if (rc) return rc;
   return 0;
 }
@@ -813,9 +814,9 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
 static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q_normalize,
                              const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
                              int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
-                             void* stream) {
+                             void* stream, const XchgOut* xo = nullptr) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
-  if (nq < 0 || (nq > 0 && (!q || (!out_packed && (!out_key || !out_ids)))))
+  if (nq < 0 || (nq > 0 && (!q || (!xo && !out_packed && (!out_key || !out_ids)))))
     return set_err(MIPS_E_INVALID, "bad q / outputs");
   if (k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "k must be in [1, %d], got %d", MIPS_MAX_K, k);
   if (nq == 0) return 0;
@@ -844,13 +845,13 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
     return set_err(MIPS_E_UNSUPPORTED, "CTA-pair tensor-core search needs a bf16 bank with d_pad <= %d (and k small enough for shared memory)", tc2::MAX_KCH * tc2::KCH);
   if (algo != MIPS_ALGO_TC && algo != MIPS_ALGO_TC128 && algo != MIPS_ALGO_TC2 && algo != MIPS_ALGO_TCX && algo != MIPS_ALGO_SIMT)
     return set_err(MIPS_E_INVALID, "unknown algo %d", algo);
+  if (xo && (algo == MIPS_ALGO_TCX || nq > (algo != MIPS_ALGO_SIMT ? h->sm_count * tc::BLOCK_M : 16384)))
+    return set_err(MIPS_E_UNSUPPORTED, "peer-memory exchange: single-chunk bf16 / SIMT searches only");
   if (h->ntotal == 0) {
     // faiss semantics on an empty index: ids -1
-    merge_topk_kernel<true><<<(nq + 3) / 4, 128, 0, st>>>(
-        nullptr, nullptr, nullptr, nullptr, 0, nq, k, k, 0, nullptr, h->metric, MIPS_OUT_IP, 0.f, nullptr,
-        out_key, out_ids, out_xnorm2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
-        static_cast<PackedCand*>(out_packed));
-    LAUNCH_CHECK("merge_topk_kernel<empty>");
+    int rc0 = launch_merge_local(h, nullptr, nullptr, nullptr, 0, nq, k, k, 0, out_key, out_ids, out_xnorm2,
+                                 out_packed, nullptr, st, "merge_topk_kernel<empty>", xo);
+    if (rc0) return rc0;
     if (out_qnorm2) CUDA_TRY(cudaMemsetAsync(out_qnorm2, 0, static_cast<size_t>(nq) * sizeof(float), st));
     return 0;
   }
@@ -865,7 +866,7 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
                           out_xnorm2 ? out_xnorm2 + static_cast<size_t>(q0) * k : nullptr,
                           out_qnorm2 ? out_qnorm2 + q0 : nullptr,
                           out_packed ? static_cast<PackedCand*>(out_packed) + static_cast<size_t>(q0) * k : nullptr,
-                          st);
+                          st, xo);
     if (rc) return rc;
   }
   return 0;
@@ -1012,6 +1013,79 @@ int mips_gather_tokens(const int32_t* store_ids, const int32_t* store_len, int64
       store_ids, store_len, n_rows, L, ids, pad_id, bos_id, eos_id, input_ids, attention_mask, memory_attention_mask,
       global_attention_mask);
   LAUNCH_CHECK("gather_tokens_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ peer-memory exchange
+int mips_xchg_alloc(int device, int64_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes <= 0) return set_err(MIPS_E_INVALID, "bad arguments");
+  CUDA_TRY(cudaSetDevice(device));
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, static_cast<size_t>(bytes)));
+  cudaError_t e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  cudaIpcMemHandle_t hnd;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hnd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return set_err(MIPS_E_CUDA, "exchange buffer: %s", cudaGetErrorString(e));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &hnd, 64);
+  *ptr = p;
+  return 0;
+}
+
+int mips_xchg_open(int device, const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return set_err(MIPS_E_INVALID, "bad arguments");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int mips_xchg_close(int device, void* ptr) {
+  if (!ptr) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int mips_xchg_free(int device, void* ptr) {
+  if (!ptr) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(ptr));
+  return 0;
+}
+
+int mips_search_local_xchg(mips_handle h, const float* q, int nq, int k, int q_normalize, const int64_t* ignore_ids,
+                           int64_t id_offset, int algo, void* const* peer_bufs, uint32_t* const* peer_flags,
+                           int n_peers, uint32_t seq, float* out_qnorm2, void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (!peer_bufs || !peer_flags || n_peers < 1 || n_peers > 32) return set_err(MIPS_E_INVALID, "bad peer arrays");
+  XchgOut xo{reinterpret_cast<PackedCand* const*>(peer_bufs), peer_flags,
+             reinterpret_cast<unsigned int*>(h->max_norm2_bits + 4), seq, n_peers};
+  return search_local_impl(h, q, nq, k, q_normalize, ignore_ids, id_offset, algo, nullptr, nullptr, nullptr,
+                           out_qnorm2, nullptr, stream, &xo);
+}
+
+int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, uint32_t seq, int nq, int k_in, int k_out,
+                    int metric, int out_mode, float phi, const float* q_norm2, const int64_t* ignore_ids, float* D,
+                    int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias, float* memory_bias,
+                    int mem_len, void* stream) {
+  if (!my_buf || !my_flags || n_ranks < 1 || n_ranks > 32) return set_err(MIPS_E_INVALID, "bad exchange buffer");
+  if (nq < 0 || k_in < 1 || k_out < 1 || k_out > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "bad merge shape");
+  if (nq == 0) return 0;
+  if (!D || !I) return set_err(MIPS_E_INVALID, "null buffers");
+  if (out_mode < MIPS_OUT_IP || out_mode > MIPS_OUT_AUGL2) return set_err(MIPS_E_INVALID, "bad out_mode %d", out_mode);
+  if ((out_mode != MIPS_OUT_IP || cosine || doc_prob || memory_bias) && !q_norm2)
+    return set_err(MIPS_E_INVALID, "q_norm2 required for L2 / cosine outputs");
+  if (memory_bias && mem_len < 1) return set_err(MIPS_E_INVALID, "mem_len must be >= 1");
+  merge_topk_kernel<false><<<(nq + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      nullptr, nullptr, nullptr, nullptr, n_ranks, nq, k_in, k_out, 0, ignore_ids, metric, out_mode, phi, q_norm2, D, I,
+      nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, static_cast<const PackedCand*>(my_buf), nullptr,
+      nullptr, 0, XchgOut{nullptr, nullptr, nullptr, 0u, 0}, XchgIn{my_flags, seq, n_ranks});
+  LAUNCH_CHECK("merge_topk_kernel<final, peer exchange>");
   return 0;
 }
 

@@ -142,6 +142,10 @@ class B200FlatIndex:
         check(self._L.mips_reconstruct(self._h, i0, n, out.ctypes.data_as(C.c_void_p), 0, self._stream()))
         return out
 
+    @staticmethod
+    def _algo_code(algo: str) -> int:
+        return _ALGOS[algo]
+
     def gather_rows(self, ids: torch.Tensor) -> torch.Tensor:
         """Stored rows by GLOBAL id, float32 [..., d] on the device: what the reference
         re-encodes per step (mips.py:465-470) when the memory encoder is frozen. ids outside this

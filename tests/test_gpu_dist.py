@@ -51,6 +51,21 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         assert np.array_equal(ids, I2)
         np.testing.assert_allclose(r["cosine"].cpu().numpy(), o.doc_scores(xq, xb[ids]), rtol=1e-4, atol=1e-5)
         assert r["memory_bias"].shape == (nq, k * 4)
+        # peer-memory exchange (CUDA IPC over NVLink, fused into the merge kernels): same answers as the
+        # NCCL all-gather, search after search (the two slot sets alternate), with and without extras
+        sh = m.ShardedFlatIndex(mp.index, dist.group.WORLD, exchange="p2p")
+        sh.counts = mp._sharded.counts
+        xq_t = torch.from_numpy(xq).cuda()
+        for it in range(5):
+            kk = k if it % 2 == 0 else 3
+            a = sh.search(xq_t, kk, want=("scores", "ids", "cosine"), out_mode=0)
+            b = mp._sharded.search(xq_t, kk, want=("scores", "ids", "cosine"), out_mode=0)
+            torch.cuda.synchronize()
+            assert torch.equal(a["ids"], b["ids"]) and torch.equal(a["scores"], b["scores"])
+            assert torch.equal(a["cosine"], b["cosine"])
+        a = sh.search(xq_t[:7], k, ignore_ids=torch.as_tensor(ign[:7]))
+        assert np.array_equal(a["ids"].cpu().numpy(), I_ref[:7])
+        sh.close()
         ret[rank] = True
     finally:
         dist.destroy_process_group()

@@ -96,3 +96,20 @@ def test_two_rank_exchange_gloo():
         ret = man.dict()
         mp.spawn(_worker, args=(world, port, 5003, 32, 9, 6, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def test_weighted_ranges_tile_the_bank_and_follow_the_weights():
+    from retrieval_augmented_mds_b200.sharded import weighted_ranges
+
+    for n, w in ((10_000_000, [1.0, 0.94, 1.03, 0.97, 1.0, 1.06, 0.99, 1.01]), (1001, [1, 1, 1]), (5, [3, 1]), (0, [1, 2])):
+        rs = weighted_ranges(n, w)
+        assert len(rs) == len(w) and rs[0].start == 0 and rs[-1].stop == n
+        assert all(a.stop == b.start for a, b in zip(rs, rs[1:]))
+    rs = weighted_ranges(8_000_000, [1.0, 0.5, 1.0, 2.0])          # clamped to +-10 % of the equal share
+    sizes = [len(r) for r in rs]
+    assert max(sizes) <= 1.2 * 2_000_000 and min(sizes) >= 0.8 * 2_000_000 and sizes[3] > sizes[0] == sizes[1]
+    rs = weighted_ranges(8_000_000, [1.00, 0.95, 1.05, 1.00])
+    sizes = [len(r) for r in rs]
+    assert sizes[2] > sizes[0] > sizes[1] and abs(sizes[2] / sizes[1] - 1.05 / 0.95) < 1e-3
+    with pytest.raises(ValueError):
+        weighted_ranges(10, [0, 0])
