@@ -98,8 +98,8 @@ __device__ __forceinline__ uint32_t pick128(const uint32_t (&v)[4][32], int c) {
 // the admission threshold; the set is only touched when a score beats it.
 template <bool kL2>
 __device__ __forceinline__ void fold_tile(uint32_t (&v)[4][32], const float* xnorm2, int id0,
-                                          int64_t ntotal, int ign, bool live, uint32_t* set, int kcap,
-                                          float& thr, int& worst) {
+                                          int64_t ntotal, int ign, bool live, uint32_t* set, int k, int kcap,
+                                          bool first, float& thr, int& worst) {
   if (kL2) {
     // ranking key for L2: <q,x> - |x|^2/2 (same address for every lane: broadcast loads)
     const float4* xn = reinterpret_cast<const float4*>(xnorm2 + id0);
@@ -125,11 +125,32 @@ __device__ __forceinline__ void fold_tile(uint32_t (&v)[4][32], const float* xno
     // ~95 KB and ncu showed 42 % of its stall samples on instruction fetch): two instructions
     // per column build a candidate bit mask, then a rolled loop visits the few set bits and
     // pulls each score out of its register through one switch.
+    int filled = 0;
+    if (first && id0 + 64 <= ntotal && (ign < id0 || ign >= id0 + k)) {
+      // first tile of the split: its first k columns ARE the top-k so far. Store them directly (static
+      // register indices, no admission calls: 128 admissions of ~300 cycles each otherwise open
+      // every launch) and let one call find the worst entry.
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        if (i < k) {
+          set[i * TOPK_STRIDE] = f32_to_ordered(__uint_as_float(v[i >> 5][i & 31]));
+          set[(kcap + i) * TOPK_STRIDE] = static_cast<uint32_t>(id0 + i);
+        }
+      }
+      const uint2 r = topk_replace(set, kcap, 0, f32_to_ordered(__uint_as_float(v[0][0])), id0);
+      thr = ordered_to_f32(r.x);
+      worst = static_cast<int>(r.y);
+      filled = k;
+    }
     uint32_t mk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int g = 0; g < 4; ++g)
 #pragma unroll
       for (int j = 0; j < 32; ++j) mk[g] |= (__uint_as_float(v[g][j]) > thr ? 1u : 0u) << j;
+    if (filled > 0) {   // columns [0, filled) are in the set already (filled <= 64)
+      mk[0] &= filled >= 32 ? 0u : ~((1u << filled) - 1u);
+      mk[1] &= filled <= 32 ? ~0u : (filled >= 64 ? 0u : ~((1u << (filled - 32)) - 1u));
+    }
     unsigned long long todo = (static_cast<unsigned long long>(mk[1]) << 32) | mk[0];
     unsigned long long later = (static_cast<unsigned long long>(mk[3]) << 32) | mk[2];
     int base = 0;
@@ -409,7 +430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(tempty0_leader + 8u * acc);   // accumulator is in registers
-      fold_tile<kL2>(v, p.xnorm2, id0, p.ntotal, ign, live, set, kcap, thr, worst);
+      fold_tile<kL2>(v, p.xnorm2, id0, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst);
     }
 
     if (live) {
