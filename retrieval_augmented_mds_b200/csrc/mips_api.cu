@@ -572,7 +572,9 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     p.n_tiles = n_tiles;
     p.n_qpairs = n_qpairs;
     p.n_splits = n_splits;
-    int skch = 4;
+    // 48 KiB stages when three of them fit (k <= 8 at d = 768), else 32 KiB: A/B on one board with pacing on,
+    // 12.16 ms vs 12.33 ms per launch on the 10M x 768 bank
+    int skch = (h->d_pad / tc2::KCH) % 6 == 0 && tc2::pick_stages(h->d_pad, k, 6) >= 3 ? 6 : 4;
     if (const char* e = getenv("MIPS_TC2_SKCH")) {   // tuning experiments only
       const int v = atoi(e);
       if (v == 2 || v == 4 || v == 6) skch = v;
@@ -835,8 +837,10 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
     return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d and k <= 32", tc2::MAX_KCH * tc2::KCH);
   if (algo == MIPS_ALGO_AUTO) {
     static const int auto_tc2 = [] { const char* e = getenv("MIPS_AUTO_TC2"); return e ? atoi(e) : 1; }();
-    // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles
-    if (tc2_ok && (auto_tc2 && nq > tc::BLOCK_M || !tc_ok)) algo = MIPS_ALGO_TC2;
+    // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles.
+    // Large k goes to the pair kernel whatever the batch: its compact unsorted-set epilogue keeps up where
+    // the sorted lists of the 1-CTA kernel do not (nq=128: k=16 3.4 vs 3.7 ms, k=32 3.6 vs 7.3 ms, k=64 4.6 vs 22.9 ms).
+    if (tc2_ok && (auto_tc2 && (nq > tc::BLOCK_M || k > 8) || !tc_ok)) algo = MIPS_ALGO_TC2;
     else algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
   }
   if ((algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128) && !tc_ok)

@@ -34,7 +34,7 @@ def test_write_read_index_round_trip(cuda_device, metric):
     assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
 
 
-def test_reference_call_sequence_through_unmodified_datasets(cuda_device, tmp_path):
+def test_reference_call_sequence_through_unmodified_datasets(cuda_device, tmp_path, monkeypatch):
     """Mips.build_index / Mips.search / Mips.save / Mips.load as the reference drives HF datasets,
     with `import faiss` resolving to the stand-in."""
     pkg.install_faiss_shim()
@@ -43,6 +43,9 @@ def test_reference_call_sequence_through_unmodified_datasets(cuda_device, tmp_pa
 
     if "b200" not in faiss.__version__:
         pytest.skip("a real faiss is installed")
+    # this image's torchvision has no torchvision.io.VideoReader, which datasets' numpy formatter imports as
+    # soon as torchvision is loaded (another test's `import transformers` loads it): unrelated to the index
+    monkeypatch.setattr(datasets.config, "TORCHVISION_AVAILABLE", False)
     xb, xq = _data(2500, 64, 9, 11)
     xb_n = o.normalize_L2(xb)
     ds = datasets.Dataset.from_dict({"embeddings": xb_n})
