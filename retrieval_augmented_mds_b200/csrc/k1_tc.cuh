@@ -21,8 +21,8 @@
 //     alone needs 384 of the 512 TMEM columns.
 //   * epilogue: thread <-> query. Each thread pulls its lane's ACC_N scores (tcgen05.ld 32x32b),
 //     releases the accumulator, takes one max over them and compares with its running k-th best;
-//     only when something beats it (rare after warm-up) does it walk the values and insert
-//     into its sorted list in shared memory. The [nq, N] score matrix never reaches HBM.
+//     only when something beats it (rare after warm-up) does it admit candidates into its unsorted
+//     top-k set in shared memory (k1_topk.cuh). The [nq, N] score matrix never reaches HBM.
 //
 // Grid = n_qtiles * n_splits CTAs (<= #SMs): CTA (qtile, split) scans bank tiles
 // [split*T/S, (split+1)*T/S) for query tile qtile; CTAs of one split run side by side so a bank
@@ -32,6 +32,7 @@
 // the bank per batch of <= 128*n_qtiles queries.
 #pragma once
 #include "common.cuh"
+#include "k1_topk.cuh"
 #include "ptx.cuh"
 
 namespace tc {
@@ -47,7 +48,7 @@ constexpr int SMEM_LIMIT = 232448;                    // 227 KiB opt-in maximum
 
 // shared memory: [align pad 1024][stages][lists][barriers]
 __host__ __device__ constexpr int box_bytes(int acc_n) { return acc_n * KCH * 2; }
-__host__ __device__ inline int list_bytes(int k) { return BLOCK_M * k * 8; }
+__host__ __device__ inline int list_bytes(int k) { return BLOCK_M * topk_kcap(k) * 8; }
 __host__ __device__ inline int bar_bytes() { return (2 * MAX_STAGES + 6) * 8; }
 // boxes (k chunks of 64) per stage: ~48 KiB stages when that divides d_pad/64, else ~32 KiB
 inline int pick_skch(int d_pad, int acc_n) {
@@ -91,8 +92,7 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
 
   const int S = p.stages;
   const uint32_t lists_off = static_cast<uint32_t>(S) * STAGE_BYTES;
-  float* list_key = reinterpret_cast<float*>(gen + lists_off);
-  int* list_id = reinterpret_cast<int*>(gen + lists_off + BLOCK_M * p.k * 4);
+  uint32_t* lists = reinterpret_cast<uint32_t*>(gen + lists_off);   // per warp: keys [kcap][32], ids [kcap][32]
   const uint32_t bars = base + lists_off + list_bytes(p.k);
   auto full_bar = [&](int i) { return bars + 8u * i; };
   auto empty_bar = [&](int i) { return bars + 8u * (MAX_STAGES + i); };
@@ -242,12 +242,13 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
       ptx::mbar_arrive(qready_bar);
     }
 
-    float* lk = list_key + row * p.k;
-    int* li = list_id + row * p.k;
-    for (int i = 0; i < p.k; ++i) {
-      lk[i] = -CUDART_INF_F;
-      li[i] = -1;
+    const int kcap = topk_kcap(p.k);
+    uint32_t* set = lists + warp * 64 * kcap + lane;   // this query's keys: key i at set[i * 32], id i at set[(kcap + i) * 32]
+    for (int i = 0; i < kcap; ++i) {
+      set[i * TOPK_STRIDE] = i < p.k ? f32_to_ordered(-CUDART_INF_F) : 0xffffffffu;   // [k, kcap): never the worst
+      set[(kcap + i) * TOPK_STRIDE] = 0xffffffffu;
     }
+    int worst = 0;
     const bool live = qrow < p.nq;
     const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
     float thr = -CUDART_INF_F;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
     for (int tile = tile0; tile < tile1; ++tile, ++it) {
       const int acc = acc_of(it);
       ptx::mbar_wait(tfull_bar(acc), acc_par(it));
-      __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent insert path
+      __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent admission path
       ptx::tc_fence_after();
       uint32_t v[NGRP][32];
 #pragma unroll
@@ -265,48 +266,14 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // accumulator is in registers: MMA may reuse it
-
-      const int id0 = tile * ACC_N;
-      if (kL2) {
-        // ranking key for L2: <q,x> - |x|^2/2 (same for every lane: broadcast loads)
-        const float4* xn = reinterpret_cast<const float4*>(p.xnorm2 + id0);
-#pragma unroll
-        for (int g = 0; g < NGRP; ++g) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(xn + g * 8 + j);
-            v[g][4 * j + 0] = __float_as_uint(__uint_as_float(v[g][4 * j + 0]) - 0.5f * t.x);
-            v[g][4 * j + 1] = __float_as_uint(__uint_as_float(v[g][4 * j + 1]) - 0.5f * t.y);
-            v[g][4 * j + 2] = __float_as_uint(__uint_as_float(v[g][4 * j + 2]) - 0.5f * t.z);
-            v[g][4 * j + 3] = __float_as_uint(__uint_as_float(v[g][4 * j + 3]) - 0.5f * t.w);
-          }
-        }
-      }
-      float m = -CUDART_INF_F;
-#pragma unroll
-      for (int g = 0; g < NGRP; ++g)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[g][j]));
-      if (m > thr && live) {
-#pragma unroll
-        for (int g = 0; g < NGRP; ++g) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(v[g][j]);
-            if (s > thr) {
-              const int id = id0 + g * 32 + j;
-              if (id < p.ntotal && id != ign) thr = topk_list_insert(lk, li, p.k, s, id);
-            }
-          }
-        }
-      }
+      fold_tile<kL2, NGRP>(v, p.xnorm2, tile * ACC_N, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst);
     }
 
     if (live) {
       const size_t o = (static_cast<size_t>(split) * p.nq + qrow) * p.k;
-      for (int i = 0; i < p.k; ++i) {
-        p.part_key[o + i] = lk[i];
-        p.part_ids[o + i] = li[i];
+      for (int i = 0; i < p.k; ++i) {   // unsorted: K2 merges by arg-max rounds
+        p.part_key[o + i] = ordered_to_f32(set[i * TOPK_STRIDE]);
+        p.part_ids[o + i] = static_cast<int>(set[(kcap + i) * TOPK_STRIDE]);
       }
     }
   }

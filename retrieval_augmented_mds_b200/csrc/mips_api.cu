@@ -647,10 +647,12 @@ static int launch_merge_local(mips_index_s* h, const float* part_key, const int*
                               int64_t* out_ids, float* out_xn2, void* out_packed, const int* q_active,
                               cudaStream_t st, const char* what, const XchgOut* xo = nullptr) {
   const int C = n_parts * k_in;
-  int cap = 0;
+  int cap = 0, wpb = 4;   // queries (warps) per block: fewer when one query's candidates need a large staging area
   if (C > 64 && C <= 6144) cap = C;
-  const size_t smem = static_cast<size_t>(4) * cap * sizeof(uint2);
-  merge_topk_kernel<true><<<(nq + 3) / 4, 128, smem, st>>>(
+  else if (C > 6144 && C <= 12288) { cap = C; wpb = 2; }
+  else if (C > 12288 && C <= 24576) { cap = C; wpb = 1; }
+  const size_t smem = static_cast<size_t>(wpb) * cap * sizeof(uint2);
+  merge_topk_kernel<true><<<(nq + wpb - 1) / wpb, 32 * wpb, smem, st>>>(
       part_key, part_ids, nullptr, bank_xn2, n_parts, nq, k_in, k_out, id_offset, nullptr, h->metric, MIPS_OUT_IP,
       0.f, nullptr, out_key, out_ids, out_xn2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
       static_cast<PackedCand*>(out_packed), q_active, cap, xo ? *xo : XchgOut{nullptr, nullptr, nullptr, 0u, 0});
@@ -837,10 +839,9 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
     return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d and k <= 32", tc2::MAX_KCH * tc2::KCH);
   if (algo == MIPS_ALGO_AUTO) {
     static const int auto_tc2 = [] { const char* e = getenv("MIPS_AUTO_TC2"); return e ? atoi(e) : 1; }();
-    // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles.
-    // Large k goes to the pair kernel whatever the batch: its compact unsorted-set epilogue keeps up where
-    // the sorted lists of the 1-CTA kernel do not (nq=128: k=16 3.4 vs 3.7 ms, k=32 3.6 vs 7.3 ms, k=64 4.6 vs 22.9 ms).
-    if (tc2_ok && (auto_tc2 && (nq > tc::BLOCK_M || k > 8) || !tc_ok)) algo = MIPS_ALGO_TC2;
+    // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles
+    // (nq=128 on 10M x 768: 2.3 / 2.6 / 3.3 ms at k = 8 / 32 / 64 vs 3.3 / 3.6 / 4.2 ms on the pair kernel)
+    if (tc2_ok && (auto_tc2 && nq > tc::BLOCK_M || !tc_ok)) algo = MIPS_ALGO_TC2;
     else algo = tc_ok ? MIPS_ALGO_TC : MIPS_ALGO_SIMT;
   }
   if ((algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128) && !tc_ok)
