@@ -36,6 +36,12 @@ static int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+// tuning knobs from the environment (A/B runs only), read once per process
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
     cudaError_t _e = (expr);                                                                    \
@@ -390,9 +396,10 @@ static int launch_ingest(mips_index_s* h, const float* x_dev, int64_t n, int64_t
                          void* out, float* norm2_out, unsigned int* maxbits, cudaStream_t st) {
   const unsigned blocks = static_cast<unsigned>((n_pad + 7) / 8);
   if (blocks == 0) return 0;
+  static const bool k0_scalar = env_int("MIPS_K0_SCALAR", 0) != 0;
   // vector path: 16-byte loads need d % 4 == 0 and 16-byte aligned rows on both sides
   const bool vec_ok = h->d % 4 == 0 && h->d_pad <= 1024 && reinterpret_cast<uintptr_t>(x_dev) % 16 == 0 &&
-                      reinterpret_cast<uintptr_t>(out) % 16 == 0 && !getenv("MIPS_K0_SCALAR");
+                      reinterpret_cast<uintptr_t>(out) % 16 == 0 && !k0_scalar;
   if (vec_ok) {
 #define K0_VEC(T, NV)                                                                                \
   ingest_rows_vec_kernel<T, NV><<<blocks, 256, 0, st>>>(x_dev, n, n_pad, h->d, h->d_pad, normalize,  \
@@ -575,10 +582,8 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     // 48 KiB stages when three of them fit (k <= 8 at d = 768), else 32 KiB: A/B on one board with pacing on,
     // 12.16 ms vs 12.33 ms per launch on the 10M x 768 bank
     int skch = (h->d_pad / tc2::KCH) % 6 == 0 && tc2::pick_stages(h->d_pad, k, 6) >= 3 ? 6 : 4;
-    if (const char* e = getenv("MIPS_TC2_SKCH")) {   // tuning experiments only
-      const int v = atoi(e);
-      if (v == 2 || v == 4 || v == 6) skch = v;
-    }
+    static const int skch_env = env_int("MIPS_TC2_SKCH", 0);   // tuning experiments only
+    if (skch_env == 2 || skch_env == 4 || skch_env == 6) skch = skch_env;
     while (skch > 2 && tc2::pick_stages(h->d_pad, k, skch) < 2) skch -= 2;
     p.stages = tc2::pick_stages(h->d_pad, k, skch);
     if (p.stages < 2)
@@ -586,7 +591,8 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     p.cache_hint = n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
     p.pace = nullptr;
     p.pace_window = 6;   // measured: HBM reads 40 GB -> ~19 GB per launch on the 10M x 768 bank; step time within +-4 % of unpaced (which side wins depends on how hard the board is power-capped)
-    if (const char* e = getenv("MIPS_TC2_PACE")) p.pace_window = atoi(e);   // tuning; <= 0 disables
+    static const int pace_env = env_int("MIPS_TC2_PACE", -1);   // tuning; 0 disables
+    if (pace_env >= 0) p.pace_window = pace_env;
     if (n_qpairs > 1 && p.pace_window > 0) {
       const size_t pb = static_cast<size_t>(n_splits) * n_qpairs * sizeof(int);
       rc = grow(&h->pace, &h->pace_bytes, pb);
@@ -772,10 +778,9 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     p.n_qtiles = n_qtiles;
     p.n_splits = n_splits;
     int skch = tc::pick_skch(h->d_pad, acc_n);
-    if (const char* e = getenv("MIPS_TC_SKCH")) {   // tuning experiments only (IP metric, 64-row accumulators)
-      const int v = atoi(e);
-      if (acc_n == 64 && !l2 && (v == 2 || v == 3 || v == 4 || v == 6 || v == 12)) skch = v;
-    }
+    static const int tc_skch_env = env_int("MIPS_TC_SKCH", 0);   // tuning experiments only (IP metric, 64-row accumulators)
+    if (acc_n == 64 && !l2 && (tc_skch_env == 2 || tc_skch_env == 3 || tc_skch_env == 4 || tc_skch_env == 6 || tc_skch_env == 12))
+      skch = tc_skch_env;
     p.stages = tc::pick_stages(k, skch, acc_n);
     // a bank tile is re-read by the other query tiles from L2; with one query tile it is dead
     p.cache_hint = n_qtiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
@@ -832,13 +837,13 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
   const bool tcx_ok = h->dtype == MIPS_DTYPE_F32 && h->shadow_valid && k <= 32 &&
                       tc2::pick_stages(h->d_pad, tcx_split_list(k), 2) >= 2;
   if (algo == MIPS_ALGO_AUTO && h->dtype == MIPS_DTYPE_F32) {
-    static const int auto_tcx = [] { const char* e = getenv("MIPS_AUTO_TCX"); return e ? atoi(e) : 1; }();
+    static const int auto_tcx = env_int("MIPS_AUTO_TCX", 1);
     algo = (tcx_ok && auto_tcx) ? MIPS_ALGO_TCX : MIPS_ALGO_SIMT;
   }
   if (algo == MIPS_ALGO_TCX && !tcx_ok)
     return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d and k <= 32", tc2::MAX_KCH * tc2::KCH);
   if (algo == MIPS_ALGO_AUTO) {
-    static const int auto_tc2 = [] { const char* e = getenv("MIPS_AUTO_TC2"); return e ? atoi(e) : 1; }();
+    static const int auto_tc2 = env_int("MIPS_AUTO_TC2", 1);
     // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles
     // (nq=128 on 10M x 768: 2.3 / 2.6 / 3.3 ms at k = 8 / 32 / 64 vs 3.3 / 3.6 / 4.2 ms on the pair kernel)
     if (tc2_ok && (auto_tc2 && nq > tc::BLOCK_M || !tc_ok)) algo = MIPS_ALGO_TC2;
