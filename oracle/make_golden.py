@@ -9,7 +9,8 @@ reference sources by AST / source segment and executed unmodified:
                              reference's inner_product), Mips._prepare_query (with
                              faiss.normalize_L2 replaced by its documented contract)
   sotasum/pretrain.py        retriever_metrics
-  sotasum/retriever_generator.py   the doc-score statements :158-172 and :188-192
+  sotasum/retriever_generator.py   the doc-score statements :158-172 and :188-192, the copy/generation
+                             mixture statements :391-404
 
 Run here (needs /root/reference):   python oracle/make_golden.py
 The .npz files are small and committed; the GPU box never reads /root/reference.
@@ -182,6 +183,24 @@ def main() -> None:
     (OUT / "doc_scores_statements.txt").write_text(
         "# statements executed from /root/reference/sotasum/retriever_generator.py\n"
         + "\n".join("# " + ln.split("=")[0].strip() for ln in code.splitlines() if "=" in ln and not ln.startswith(" ")))
+    # ---- G7: generation / copy mixture of RetrieverGenerator.forward (retriever_generator.py:391-404)
+    code = _statements(rg, 391, 397) + "\n" + _statements(rg, 404, 404)
+    rng7 = np.random.default_rng(7070)
+    B, T, V, S = 3, 4, 97, 21
+    import torch.nn.functional as F
+    logits = torch.tensor(rng7.standard_normal((B, T, V), dtype=np.float32) * 3.0)
+    gates = torch.softmax(torch.tensor(rng7.standard_normal((B, T, 2), dtype=np.float32)), -1)
+    gen_gate, copy_gate = gates.chunk(2, dim=-1)                       # decoder_own.py:536
+    align = torch.softmax(torch.tensor(rng7.standard_normal((B, T, S), dtype=np.float32)), -1)
+    copy_probs = copy_gate * align                                       # decoder_own.py:538
+    copy_seq = torch.tensor(rng7.integers(0, V, (B, S)))
+    copy_seq[:, :4] = copy_seq[:, 4:8]                                   # repeated tokens accumulate
+    ns = {"torch": torch, "F": F, "gen_gate": gen_gate, "copy_probs": copy_probs,
+          "decoder_outputs": types.SimpleNamespace(logits=logits.clone()),
+          "decoder_hidden_states": torch.zeros(B, T, 8), "encoder_copy_sequence": copy_seq}
+    exec(compile(code, str(rg), "exec"), ns)
+    np.savez_compressed(OUT / "copy_mixture.npz", logits=logits.numpy(), gen_gate=gen_gate.numpy(),
+                        copy_probs=copy_probs.numpy(), copy_seq=copy_seq.numpy(), outs=ns["outs"].numpy())
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*.npz")):
         print(f"  {f.name}: {f.stat().st_size/1024:.1f} KiB")

@@ -188,6 +188,22 @@ def doc_prob(mips_scores: np.ndarray, beta: float = 1.0, beta_bias: float = 0.0)
     return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
 
 
+def copy_mixture(logits: np.ndarray, gen_gate: np.ndarray, copy_probs: np.ndarray, copy_seq: np.ndarray,
+                 eps: float = 1e-7) -> np.ndarray:
+    """retriever_generator.py:391-404: log(gen_gate * softmax(logits) + scatter_add(copy_probs at
+    copy_seq) + 1e-7). logits [B, T, V], gen_gate [B, T, 1], copy_probs [B, T, S] (already gated,
+    decoder_own.py:538), copy_seq int [B, S] -> [B, T, V]. float32 like the reference."""
+    x = logits.astype(np.float32)
+    x = x - x.max(-1, keepdims=True)
+    e = np.exp(x)
+    probs = (gen_gate.astype(np.float32) * (e / e.sum(-1, keepdims=True))).astype(np.float32)
+    B, T, _ = probs.shape
+    for b in range(B):
+        for t in range(T):
+            np.add.at(probs[b, t], copy_seq[b], copy_probs[b, t].astype(np.float32))
+    return np.log(probs + np.float32(eps)).astype(np.float32)
+
+
 def retriever_metrics(pred: np.ndarray, counts: np.ndarray) -> dict:
     """pretrain.py:69-85 (copy at retriever_lightning.py:71-87), including the reference's
     reciprocal-rank quirk (1/argmax, inf -> 0: a rank-1 hit scores 0)."""

@@ -22,6 +22,7 @@
 #include "k3_rerank.cuh"
 #include "k4_metrics.cuh"
 #include "k5_gather.cuh"
+#include "k6_mixture.cuh"
 #include "mips_b200.h"
 
 // ------------------------------------------------------------------------------------------
@@ -1096,6 +1097,29 @@ int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, u
       nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, static_cast<const PackedCand*>(my_buf), nullptr,
       nullptr, 0, XchgOut{nullptr, nullptr, nullptr, 0u, 0}, XchgIn{my_flags, seq, n_ranks});
   LAUNCH_CHECK("merge_topk_kernel<final, peer exchange>");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ mixture
+int mips_copy_mixture(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
+                      int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, void* stream) {
+  if (n_rows < 0 || rows_per_batch < 1 || V < 1 || S < 0) return set_err(MIPS_E_INVALID, "bad shape");
+  if (n_rows == 0) return 0;
+  if (n_rows % rows_per_batch != 0) return set_err(MIPS_E_INVALID, "n_rows must be a multiple of rows_per_batch");
+  if (!logits || !gen_gate || !out || (S > 0 && (!copy_probs || !copy_seq))) return set_err(MIPS_E_INVALID, "null buffers");
+  if (V > mix::MAX_V)
+    return set_err(MIPS_E_UNSUPPORTED, "vocabulary of %d does not fit one CTA's shared memory (max %d)", V, mix::MAX_V);
+  if (n_rows > 0x7fffffff) return set_err(MIPS_E_INVALID, "too many rows");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  mix::MAX_V * static_cast<int>(sizeof(float))));
+    attr_set = true;
+  }
+  mix::copy_mixture_kernel<<<static_cast<unsigned>(n_rows), mix::THREADS, static_cast<size_t>(V) * sizeof(float),
+                             static_cast<cudaStream_t>(stream)>>>(logits, gen_gate, copy_probs, copy_seq,
+                                                                  rows_per_batch, V, S, eps, out);
+  LAUNCH_CHECK("copy_mixture_kernel");
   return 0;
 }
 

@@ -228,3 +228,30 @@ def test_double_buffered_refresh_serves_old_bank_until_commit(cuda_device):
     mips.commit_refresh(200)
     s2, i2 = mips.search(xq, None, 5)
     assert np.array_equal(np.asarray(i2), np.asarray(i_old))
+
+
+# ----------------------------------------------------------------------------------------- N3 (forward)
+def test_copy_mixture_matches_reference_statements(cuda_device, golden):
+    """Golden from retriever_generator.py:391-404 executed on seeded tensors, then a BART-sized vocabulary
+    against the oracle and against the reference's own sequence of torch ops on the GPU."""
+    g = golden["copy_mixture"]
+    out = pkg.copy_mixture(*(torch.from_numpy(g[k]).cuda() for k in ("logits", "gen_gate", "copy_probs", "copy_seq")))
+    np.testing.assert_allclose(out.cpu().numpy(), g["outs"], rtol=1e-5, atol=1e-5)
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    B, T, V, S = 2, 5, 50265, 2560                                   # k * L = 5 * 512 memory positions
+    logits = torch.randn((B, T, V), generator=gen, device=cuda_device) * 4
+    gates = torch.softmax(torch.randn((B, T, 2), generator=gen, device=cuda_device), -1)
+    copy_probs = gates[..., 1:] * torch.softmax(torch.randn((B, T, S), generator=gen, device=cuda_device), -1)
+    copy_seq = torch.randint(0, V, (B, S), generator=gen, device=cuda_device)
+    copy_seq[:, :100] = copy_seq[:, 100:200]                         # repeated tokens accumulate
+    out = pkg.copy_mixture(logits, gates[..., :1], copy_probs, copy_seq)
+    probs = gates[..., :1] * torch.softmax(logits, -1)               # the reference's ops, on the GPU
+    probs.scatter_add_(-1, copy_seq.reshape(B, 1, -1).expand(-1, T, -1), copy_probs)
+    torch.testing.assert_close(out, torch.log(probs + 1e-7), rtol=1e-5, atol=1e-5)
+    want = o.copy_mixture(logits.cpu().numpy(), gates[..., :1].cpu().numpy(), copy_probs.cpu().numpy(), copy_seq.cpu().numpy())
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=2e-5)
+    # a distribution up to the reference's +1e-7 per vocabulary entry: total mass 1 + V * 1e-7
+    assert bool(torch.allclose(torch.logsumexp(out, -1), torch.full((B, T), float(np.log1p(V * 1e-7)), device=cuda_device), atol=1e-4))
+    with pytest.raises(pkg._lib.MipsError, match="shared memory"):
+        pkg.copy_mixture(torch.zeros((1, 1, 60000), device=cuda_device), torch.ones((1, 1, 1), device=cuda_device),
+                         torch.zeros((1, 1, 4), device=cuda_device), torch.zeros((1, 4), dtype=torch.int64, device=cuda_device))

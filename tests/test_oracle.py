@@ -144,3 +144,11 @@ def test_check_topk_detects_errors():
     a, b = np.where(I2[1] == I[1, 0])[0][0], pos[0]
     swap[1, a], swap[1, b] = I2[1, b], I2[1, a]
     assert o.check_topk(xb2, xq, D2, swap) == 2
+
+
+def test_copy_mixture_matches_reference_statements(golden):
+    """Golden: retriever_generator.py:391-404 executed on seeded tensors (oracle/make_golden.py G7)."""
+    g = golden["copy_mixture"]
+    out = o.copy_mixture(g["logits"], g["gen_gate"], g["copy_probs"], g["copy_seq"])
+    np.testing.assert_allclose(out, g["outs"], rtol=2e-6, atol=2e-6)
+    assert np.all(np.isfinite(out))
