@@ -614,6 +614,60 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     return 0;
 }
 
+// K1, 1-CTA tensor-core kernel over a bf16 row matrix described by `tmap` (boxes of acc_n rows): the bf16 bank,
+// or the bf16 shadow of an fp32 bank. Leaves [n_splits, nq, k] candidate sets in h->part_key / part_ids.
+static int launch_tc(mips_index_s* h, const CUtensorMap& tmap, const __nv_bfloat16* q_bf16, int nq, int nq_pad, int k,
+                     int acc_n, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out) {
+    const int n_tiles = static_cast<int>((h->ntotal + acc_n - 1) / acc_n);
+    const int n_qtiles = nq_pad / tc::BLOCK_M;
+    int n_splits = std::max(1, std::min(h->sm_count / n_qtiles, n_tiles));
+    *n_parts_out = n_splits;
+    const size_t pk = static_cast<size_t>(n_splits) * nq * k;
+    int rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+    if (rc) return rc;
+    rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
+    if (rc) return rc;
+    tc::Params p;
+    p.q = q_bf16;
+    p.xnorm2 = h->norm2;
+    p.ignore_local = ign_local;
+    p.part_key = h->part_key;
+    p.part_ids = h->part_ids;
+    p.ntotal = h->ntotal;
+    p.nq = nq;
+    p.d_pad = h->d_pad;
+    p.k = k;
+    p.n_tiles = n_tiles;
+    p.n_qtiles = n_qtiles;
+    p.n_splits = n_splits;
+    int skch = tc::pick_skch(h->d_pad, acc_n);
+    static const int tc_skch_env = env_int("MIPS_TC_SKCH", 0);   // tuning experiments only (IP metric, 64-row accumulators)
+    if (acc_n == 64 && !l2 && (tc_skch_env == 2 || tc_skch_env == 3 || tc_skch_env == 4 || tc_skch_env == 6 || tc_skch_env == 12))
+      skch = tc_skch_env;
+    p.stages = tc::pick_stages(k, skch, acc_n);
+    // a bank tile is re-read by the other query tiles from L2; with one query tile it is dead
+    p.cache_hint = n_qtiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+    const size_t smem = tc::smem_bytes(k, p.stages, skch, acc_n);
+    const unsigned grid = static_cast<unsigned>(n_qtiles * n_splits);
+#define TC_LAUNCH(N, K, MAP)                                                               \
+  do {                                                                                     \
+    if (l2) tc::search_tc_kernel<true, N, K><<<grid, tc::THREADS, smem, st>>>(MAP, p);     \
+    else    tc::search_tc_kernel<false, N, K><<<grid, tc::THREADS, smem, st>>>(MAP, p);    \
+  } while (0)
+    if (acc_n == 128) {
+      if (skch == 3) TC_LAUNCH(128, 3, tmap); else TC_LAUNCH(128, 2, tmap);
+    } else {
+      if (skch == 6) TC_LAUNCH(64, 6, tmap);
+      else if (skch == 12) tc::search_tc_kernel<false, 64, 12><<<grid, tc::THREADS, smem, st>>>(tmap, p);
+      else if (skch == 3) tc::search_tc_kernel<false, 64, 3><<<grid, tc::THREADS, smem, st>>>(tmap, p);
+      else if (skch == 2) tc::search_tc_kernel<false, 64, 2><<<grid, tc::THREADS, smem, st>>>(tmap, p);
+      else TC_LAUNCH(64, 4, tmap);
+    }
+#undef TC_LAUNCH
+    LAUNCH_CHECK("search_tc_kernel");
+    return 0;
+}
+
 // K1, exact fp32-FMA kernel over the stored rows (any dtype). `tile_active` (device, one int per
 // 64-query tile, or null) restricts the launch to the query tiles that need recomputing.
 static int launch_simt(mips_index_s* h, int nq, int k, const int* ign_local, bool l2, const int* tile_active,
@@ -724,7 +778,12 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     shadow_rows_kernel<<<static_cast<unsigned>((nq_pad + 7) / 8), 256, 0, st>>>(
         static_cast<const float*>(h->q_prep), nq_pad, h->d_pad, h->q_hi, h->q_res2, nullptr, nullptr);
     LAUNCH_CHECK("shadow_rows_kernel<queries>");
-    rc = launch_tc2(h, h->tmap_shadow64, h->q_hi, nq, nq_pad, m, ign_local, l2, st, &n_parts);
+    // small batches are HBM bound: the 1-CTA kernel streams the shadow as fast as the pair kernel and does
+    // not pad the batch to 256 queries
+    if (nq <= tc::BLOCK_M && h->d_pad <= tc::MAX_DPAD)
+      rc = launch_tc(h, h->tmap_shadow64, h->q_hi, nq, round_up_i(nq, tc::BLOCK_M), m, 64, ign_local, l2, st, &n_parts);
+    else
+      rc = launch_tc2(h, h->tmap_shadow64, h->q_hi, nq, nq_pad, m, ign_local, l2, st, &n_parts);
     if (rc) return rc;
     rc = launch_merge_local(h, h->part_key, h->part_ids, nullptr, n_parts, nq, m, kc, 0, h->cand_key, h->cand_rows,
                             nullptr, nullptr, nullptr, st, "merge_topk_kernel<candidates>");
@@ -756,53 +815,9 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     h->last_algo = "tc2";
   } else if (use_tc) {
     const int acc_n = algo == MIPS_ALGO_TC128 ? 128 : 64;
-    const int n_tiles = static_cast<int>((h->ntotal + acc_n - 1) / acc_n);
-    const int n_qtiles = nq_pad / tc::BLOCK_M;
-    int n_splits = std::max(1, std::min(h->sm_count / n_qtiles, n_tiles));
-    n_parts = n_splits;
-    const size_t pk = static_cast<size_t>(n_parts) * nq * k;
-    rc = grow(&h->part_key, &h->part_key_bytes, pk * sizeof(float));
+    rc = launch_tc(h, acc_n == 128 ? h->tmap128 : h->tmap64, static_cast<const __nv_bfloat16*>(h->q_prep), nq, nq_pad, k,
+                   acc_n, ign_local, l2, st, &n_parts);
     if (rc) return rc;
-    rc = grow(&h->part_ids, &h->part_ids_bytes, pk * sizeof(int));
-    if (rc) return rc;
-    tc::Params p;
-    p.q = static_cast<const __nv_bfloat16*>(h->q_prep);
-    p.xnorm2 = h->norm2;
-    p.ignore_local = ign_local;
-    p.part_key = h->part_key;
-    p.part_ids = h->part_ids;
-    p.ntotal = h->ntotal;
-    p.nq = nq;
-    p.d_pad = h->d_pad;
-    p.k = k;
-    p.n_tiles = n_tiles;
-    p.n_qtiles = n_qtiles;
-    p.n_splits = n_splits;
-    int skch = tc::pick_skch(h->d_pad, acc_n);
-    static const int tc_skch_env = env_int("MIPS_TC_SKCH", 0);   // tuning experiments only (IP metric, 64-row accumulators)
-    if (acc_n == 64 && !l2 && (tc_skch_env == 2 || tc_skch_env == 3 || tc_skch_env == 4 || tc_skch_env == 6 || tc_skch_env == 12))
-      skch = tc_skch_env;
-    p.stages = tc::pick_stages(k, skch, acc_n);
-    // a bank tile is re-read by the other query tiles from L2; with one query tile it is dead
-    p.cache_hint = n_qtiles > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
-    const size_t smem = tc::smem_bytes(k, p.stages, skch, acc_n);
-    const unsigned grid = static_cast<unsigned>(n_qtiles * n_splits);
-#define TC_LAUNCH(N, K, MAP)                                                               \
-  do {                                                                                     \
-    if (l2) tc::search_tc_kernel<true, N, K><<<grid, tc::THREADS, smem, st>>>(MAP, p);     \
-    else    tc::search_tc_kernel<false, N, K><<<grid, tc::THREADS, smem, st>>>(MAP, p);    \
-  } while (0)
-    if (acc_n == 128) {
-      if (skch == 3) TC_LAUNCH(128, 3, h->tmap128); else TC_LAUNCH(128, 2, h->tmap128);
-    } else {
-      if (skch == 6) TC_LAUNCH(64, 6, h->tmap64);
-      else if (skch == 12) tc::search_tc_kernel<false, 64, 12><<<grid, tc::THREADS, smem, st>>>(h->tmap64, p);
-      else if (skch == 3) tc::search_tc_kernel<false, 64, 3><<<grid, tc::THREADS, smem, st>>>(h->tmap64, p);
-      else if (skch == 2) tc::search_tc_kernel<false, 64, 2><<<grid, tc::THREADS, smem, st>>>(h->tmap64, p);
-      else TC_LAUNCH(64, 4, h->tmap64);
-    }
-#undef TC_LAUNCH
-    LAUNCH_CHECK("search_tc_kernel");
     h->last_algo = acc_n == 128 ? "tc128" : "tc";
   } else {
     rc = launch_simt(h, nq, k, ign_local, l2, nullptr, st, &n_parts);
