@@ -241,7 +241,7 @@ int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, u
  * with r = b * rows_per_batch + t, logits / out fp32 [n_rows, V], gen_gate [n_rows], copy_probs [n_rows, S]
  * (already gated: copy_gate * attention, decoder_own.py:538), copy_seq int64 [n_rows / rows_per_batch, S]
  * (tokens outside [0, V) are skipped), eps = 1e-7 in the reference. One pass over the logits, the
- * vocabulary row lives in shared memory: V <= 57000. Forward only (generation / evaluation); all
+ * vocabulary row lives in shared memory: V <= 56000. Forward only (generation / evaluation); all
  * pointers device memory; async on `stream`. */
 int mips_copy_mixture(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
                       int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, void* stream);

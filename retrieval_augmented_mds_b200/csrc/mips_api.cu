@@ -1128,10 +1128,11 @@ int mips_copy_mixture(const float* logits, const float* gen_gate, const float* c
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mix::MAX_V * static_cast<int>(sizeof(float))));
+                                  mix::MAX_HALF * static_cast<int>(sizeof(float))));
     attr_set = true;
   }
-  mix::copy_mixture_kernel<<<static_cast<unsigned>(n_rows), mix::THREADS, static_cast<size_t>(V) * sizeof(float),
+  if (n_rows > 0x3fffffff) return set_err(MIPS_E_INVALID, "too many rows");
+  mix::copy_mixture_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS, static_cast<size_t>((V + 1) / 2) * sizeof(float),
                              static_cast<cudaStream_t>(stream)>>>(logits, gen_gate, copy_probs, copy_seq,
                                                                   rows_per_batch, V, S, eps, out);
   LAUNCH_CHECK("copy_mixture_kernel");
