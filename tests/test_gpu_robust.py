@@ -72,3 +72,21 @@ def test_search_is_cuda_graph_capturable(cuda_device, dtype, nq):
         torch.cuda.synchronize()
         eager = idx.search_ex(q, k)
         assert torch.equal(out["ids"], eager["ids"]) and torch.equal(out["scores"], eager["scores"])
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_very_large_query_batches_are_chunked(cuda_device, dtype):
+    """More queries than one launch takes (148 SMs x 128): 74 query pairs per launch with a single bank
+    split each (pacing across more pairs than a warp tracks), then a second chunk."""
+    rng = np.random.default_rng(9)
+    n, d, nq, k = 3000, 64, 20000, 4
+    xb = rng.standard_normal((n, d), dtype=np.float32)
+    xq = rng.standard_normal((nq, d), dtype=np.float32)
+    idx = pkg.B200FlatIndex(d, 0, dtype=dtype)
+    idx.add(xb)
+    r = idx.search_ex(torch.from_numpy(xq), k)
+    torch.cuda.synchronize()
+    stored, qq = (xb, xq) if dtype == "fp32" else (o.bf16_round(xb), o.bf16_round(xq))
+    D_ref, I_ref = o.exact_topk_f64(stored, qq, k)
+    o.check_topk(stored, qq, r["scores"].cpu().numpy(), r["ids"].cpu().numpy(), 0,
+                 rtol=1e-5 if dtype == "fp32" else 1e-4, D_ref=D_ref, I_ref=I_ref, what=f"chunked {dtype}")
