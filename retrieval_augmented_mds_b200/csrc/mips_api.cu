@@ -594,7 +594,8 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     p.pace_window = 6;   // measured: HBM reads 40 GB -> ~19 GB per launch on the 10M x 768 bank; step time within +-4 % of unpaced (which side wins depends on how hard the board is power-capped)
     static const int pace_env = env_int("MIPS_TC2_PACE", -1);   // tuning; 0 disables
     if (pace_env >= 0) p.pace_window = pace_env;
-    if (n_qpairs > 1 && p.pace_window > 0) {
+    // with two pairs per split the stalls cost more than the L2 hits save (nq=512: 7.03 ms unpaced vs 7.62 ms)
+    if (n_qpairs >= 4 && p.pace_window > 0) {
       const size_t pb = static_cast<size_t>(n_splits) * n_qpairs * sizeof(int);
       rc = grow(&h->pace, &h->pace_bytes, pb);
       if (rc) return rc;
