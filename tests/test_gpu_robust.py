@@ -90,3 +90,36 @@ def test_very_large_query_batches_are_chunked(cuda_device, dtype):
     D_ref, I_ref = o.exact_topk_f64(stored, qq, k)
     o.check_topk(stored, qq, r["scores"].cpu().numpy(), r["ids"].cpu().numpy(), 0,
                  rtol=1e-5 if dtype == "fp32" else 1e-4, D_ref=D_ref, I_ref=I_ref, what=f"chunked {dtype}")
+
+
+def test_full_size_bank_properties(cuda_device):
+    """BASELINE config 3 at its FULL size (10M x 768 bf16, 1024 queries, k=8) through size-independent
+    properties: planted neighbours come first, scores descend, ids are distinct and valid, and the
+    answer equals the merge of two half banks searched separately (top-k of a union = merge of the
+    parts' top-k: the identity the row-sharded search relies on)."""
+    n, d, nq, k = 10_000_000, 768, 1024, 8
+    gen = torch.Generator(device=cuda_device).manual_seed(2024)
+    full = pkg.B200FlatIndex(d, 0, dtype="bf16", capacity=n)
+    lo = pkg.B200FlatIndex(d, 0, dtype="bf16", capacity=n // 2)
+    hi = pkg.B200FlatIndex(d, 0, dtype="bf16", capacity=n // 2, id_offset=n // 2)
+    planted_rows = torch.randint(0, n, (nq,), generator=gen, device=cuda_device)
+    xq = torch.empty((nq, d), device=cuda_device)
+    chunk = 500_000
+    for s in range(0, n, chunk):
+        blk = torch.randn((chunk, d), generator=gen, device=cuda_device)
+        sel = (planted_rows >= s) & (planted_rows < s + chunk)
+        if bool(sel.any()):
+            xq[sel] = blk[planted_rows[sel] - s].bfloat16().float() * 1.5   # the planted row wins by a wide margin
+        full.add(blk)
+        (lo if s < n // 2 else hi).add(blk)
+    r = full.search_ex(xq, k)
+    ids, sc = r["ids"], r["scores"]
+    assert full.last_algo == "tc2"
+    assert torch.equal(ids[:, 0], planted_rows)
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all()) and int(ids.min()) >= 0 and int(ids.max()) < n
+    assert all(len(set(row)) == k for row in ids[:64].cpu().tolist())
+    p_lo, qn2 = lo.search_local_packed(xq, k)
+    p_hi, _ = hi.search_local_packed(xq, k)
+    merged = full.merge_packed(torch.stack([p_lo, p_hi]), qn2, k)
+    assert torch.equal(merged["ids"], ids)
+    torch.testing.assert_close(merged["scores"], sc, rtol=1e-5, atol=1e-3)
