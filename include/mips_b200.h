@@ -43,7 +43,7 @@ typedef struct mips_index_s* mips_handle;
 #define MIPS_ALGO_TC 2     /* tcgen05/TMEM/TMA kernel, bf16 bank, d_pad <= 768:
                               2 x 64-row double-buffered TMEM accumulators (default) */
 #define MIPS_ALGO_TC128 3  /* same kernel, one 128-row accumulator (A/B comparison) */
-#define MIPS_ALGO_TCX 5    /* fp32 bank, k <= 32, d_pad <= 1024: EXACT search at tensor-core speed — TC2 over
+#define MIPS_ALGO_TCX 5    /* fp32 bank, d_pad <= 1024: EXACT search at tensor-core speed — TC2 over
                               a bf16 shadow of the rows keeps kc > k candidates, their keys are recomputed
                               from the fp32 rows, a rigorous error bound certifies the top-k, and queries
                               that fail it (ties at the boundary) are recomputed by SIMT. AUTO on fp32. */

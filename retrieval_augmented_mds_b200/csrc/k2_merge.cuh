@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     int stage_cap = 0,                            // LOCAL: shared-memory staging entries per warp (dynamic smem)
     XchgOut xo = XchgOut{nullptr, nullptr, nullptr, 0u, 0},   // LOCAL: publish to the peers
     XchgIn xi = XchgIn{nullptr, 0u, 0}) {                     // FINAL: wait for the peers
-  __shared__ float s_key[4][MIPS_MAX_K];
-  __shared__ float s_xn2[4][MIPS_MAX_K];
-  __shared__ float s_cos[4][MIPS_MAX_K];
+  // 2 * MIPS_MAX_K: the candidate merge of the exact fp32 search keeps up to 128 entries per query
+  __shared__ float s_key[4][2 * MIPS_MAX_K];
+  __shared__ float s_xn2[4][2 * MIPS_MAX_K];
+  __shared__ float s_cos[4][2 * MIPS_MAX_K];
   __shared__ unsigned int s_hist[4][256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + w;   // 4 queries per block, fewer when the staging area is large

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) shadow_rows_kernel(const float* __restric
   }
 }
 
-// One block (8 warps) per query: exact keys of its kc <= 64 candidates, top-k, certificate.
+// One block (8 warps) per query: exact keys of its kc <= 128 candidates, top-k, certificate.
 template <bool kL2>
 __global__ void __launch_bounds__(256) rerank_exact_kernel(
     const float* __restrict__ q_prep,      // [nq_pad, d_pad] prepared fp32 queries
@@ -72,9 +72,11 @@ __global__ void __launch_bounds__(256) rerank_exact_kernel(
     int* __restrict__ need_fallback,       // [nq]
     int* __restrict__ tile_flag,           // [ceil(nq / 64)] SIMT query tiles to recompute
     int* __restrict__ n_fallback) {        // device counter (statistics)
-  __shared__ float s_exact[MIPS_MAX_K];
-  __shared__ float s_approx[MIPS_MAX_K];
-  __shared__ int s_row[MIPS_MAX_K];
+  constexpr int KC_MAX = 2 * MIPS_MAX_K;   // candidates per query
+  constexpr int PER_LANE = KC_MAX / 32;
+  __shared__ float s_exact[KC_MAX];
+  __shared__ float s_approx[KC_MAX];
+  __shared__ int s_row[KC_MAX];
   __shared__ float s_t0[8];
   const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // T0: a row that its split dropped has an approximate key <= that split's m-th best (the lowest
@@ -118,20 +120,24 @@ __global__ void __launch_bounds__(256) rerank_exact_kernel(
   __syncthreads();
   if (warp != 0) return;
 
-  // lane l owns candidates l and l + 32
-  float ek[2], ak[2];
-  int er[2];
+  // lane l owns candidates l, l + 32, l + 64, l + 96
+  float ek[PER_LANE], ak[PER_LANE];
+  int er[PER_LANE];
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
+  for (int t = 0; t < PER_LANE; ++t) {
     const int c = lane + 32 * t;
     const bool in = c < kc && s_row[c] >= 0;
     ek[t] = in ? s_exact[c] : -CUDART_INF_F;
     ak[t] = in ? s_approx[c] : CUDART_INF_F;
     er[t] = in ? s_row[c] : -1;
   }
-  const int n_valid = __popc(__ballot_sync(0xffffffffu, er[0] >= 0)) + __popc(__ballot_sync(0xffffffffu, er[1] >= 0));
+  int n_valid = 0;
+#pragma unroll
+  for (int t = 0; t < PER_LANE; ++t) n_valid += __popc(__ballot_sync(0xffffffffu, er[t] >= 0));
   // T1: a row that reached the merge but not the kc candidates has an approximate key <= the kc-th
-  float t_min = fminf(ak[0], ak[1]);
+  float t_min = CUDART_INF_F;
+#pragma unroll
+  for (int t = 0; t < PER_LANE; ++t) t_min = fminf(t_min, ak[t]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t_min = fminf(t_min, __shfl_xor_sync(0xffffffffu, t_min, o));
   float t_bound = n_valid == kc ? t_min : -CUDART_INF_F;
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(256) rerank_exact_kernel(
     float bk = -CUDART_INF_F;
     int br = 0x7fffffff;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < PER_LANE; ++t) {
       if (er[t] < 0) continue;
       const bool after = ek[t] < prev_key || (ek[t] == prev_key && er[t] > prev_row);
       if (after && (ek[t] > bk || (ek[t] == bk && er[t] < br))) {

@@ -724,7 +724,7 @@ static int launch_merge_local(mips_index_s* h, const float* part_key, const int*
 
 // candidates kept by the tensor-core filter of the exact search: enough head room between the k-th
 // exact key and the kc-th approximate key for the certificate to hold on non-degenerate data
-static int tcx_candidates(int k) { return std::min(MIPS_MAX_K, std::max(4 * k, k + 16)); }
+static int tcx_candidates(int k) { return std::min(2 * MIPS_MAX_K, std::max(4 * k, k + 16)); }
 // entries each bank split keeps for the filter: a split rarely holds more than a few of the global
 // candidates, and whatever it drops is covered by the certificate (its threshold enters T)
 static int tcx_split_list(int k) { return std::max(k, 16); }
@@ -851,14 +851,14 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
   const bool tc_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc::MAX_DPAD && h->tmap_valid;
   const bool tc2_ok = h->dtype == MIPS_DTYPE_BF16 && h->d_pad <= tc2::MAX_KCH * tc2::KCH && h->tmap_valid &&
                       tc2::pick_stages(h->d_pad, k, 2) >= 2;
-  const bool tcx_ok = h->dtype == MIPS_DTYPE_F32 && h->shadow_valid && k <= 32 &&
+  const bool tcx_ok = h->dtype == MIPS_DTYPE_F32 && h->shadow_valid &&
                       tc2::pick_stages(h->d_pad, tcx_split_list(k), 2) >= 2;
   if (algo == MIPS_ALGO_AUTO && h->dtype == MIPS_DTYPE_F32) {
     static const int auto_tcx = env_int("MIPS_AUTO_TCX", 1);
     algo = (tcx_ok && auto_tcx) ? MIPS_ALGO_TCX : MIPS_ALGO_SIMT;
   }
   if (algo == MIPS_ALGO_TCX && !tcx_ok)
-    return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d and k <= 32", tc2::MAX_KCH * tc2::KCH);
+    return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d (and k small enough for shared memory)", tc2::MAX_KCH * tc2::KCH);
   if (algo == MIPS_ALGO_AUTO) {
     static const int auto_tc2 = env_int("MIPS_AUTO_TC2", 1);
     // the CTA pair pays off once both CTAs hold live queries; small batches are HBM bound on 1-CTA tiles

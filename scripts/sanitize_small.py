@@ -25,8 +25,6 @@ for d, n, nq, k in ((768, 1500, 260, 8), (100, 777, 37, 5), (1024, 900, 130, 16)
             for algo in algos:
                 if algo == "tc" and d > 768:
                     continue
-                if algo == "tcx" and k > 32:
-                    continue
                 r = idx.search_ex(torch.from_numpy(xq), k, ignore_ids=ign, algo=algo,
                                   want=("scores", "ids", "cosine", "doc_prob", "memory_bias"), L=7)
                 torch.cuda.synchronize()

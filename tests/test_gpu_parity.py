@@ -77,8 +77,8 @@ def test_fp32_search_is_exact(m, metric, n, d, nq, k):
     idx = m.B200FlatIndex(d, metric, dtype="fp32")
     idx.add(xb)
     r = _search_np(idx, xq, k)
-    # AUTO on an fp32 bank: tensor-core filter + exact re-rank + certificate for k <= 32, SIMT above
-    assert idx.last_algo == ("tcx" if k <= 32 else "simt")
+    # AUTO on an fp32 bank: tensor-core filter + exact re-rank + certificate (SIMT only as its fallback)
+    assert idx.last_algo == "tcx"
     n_diff = o.check_topk(xb, xq, r["scores"], r["ids"], metric, rtol=RTOL_F32, what=f"fp32 m{metric}")
     assert n_diff <= max(1, nq * k // 500)
     D, I = idx.search(xq, k)  # numpy in/out = the host end-to-end entry point
