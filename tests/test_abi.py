@@ -70,3 +70,22 @@ def test_argument_validation_without_device():
         _lib.check(-1)
     with pytest.raises(_lib.MipsError):
         _lib.check(-2)
+
+
+def test_c_host_example_compiles_and_links_against_the_abi(tmp_path):
+    """include/mips_b200.h is plain C99 and examples/c_abi_demo.c links against the in-tree library with
+    gcc alone. Without a GPU the program must fail loudly (mips_create reports the missing device)."""
+    import shutil, subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    build.build()
+    exe = tmp_path / "c_abi_demo"
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"),
+           str(ROOT / "examples" / "c_abi_demo.c"), "-L", str(build.PKG_DIR), "-lmips_b200",
+           f"-Wl,-rpath,{build.PKG_DIR}", "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    if not torch.cuda.is_available():
+        run = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert run.returncode == 1 and "mips_b200:" in run.stderr    # no device: loud failure, no CPU path

@@ -255,3 +255,23 @@ def test_copy_mixture_matches_reference_statements(cuda_device, golden):
     with pytest.raises(pkg._lib.MipsError, match="shared memory"):
         pkg.copy_mixture(torch.zeros((1, 1, 60000), device=cuda_device), torch.ones((1, 1, 1), device=cuda_device),
                          torch.zeros((1, 1, 4), device=cuda_device), torch.zeros((1, 4), dtype=torch.int64, device=cuda_device))
+
+
+def test_c_host_program_runs_through_the_abi_alone(cuda_device, tmp_path):
+    """examples/c_abi_demo.c: no Python, no torch in the process — create / add / search_host from C."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    from retrieval_augmented_mds_b200 import build
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "c_abi_demo"
+    subprocess.run([gcc, "-std=c99", "-I", str(root / "include"), str(root / "examples" / "c_abi_demo.c"), "-L",
+                    str(build.PKG_DIR), "-lmips_b200", f"-Wl,-rpath,{build.PKG_DIR}", "-o", str(exe)], check=True)
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "query 3:  300 (" in run.stdout and "kernel: tcx" in run.stdout
