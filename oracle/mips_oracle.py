@@ -9,7 +9,8 @@ path. The oracle is therefore pinned against OUTPUTS OF TH
 CODE run in the build container: oracle/make_golden.py AST-extracts `inner_product`,
 `get_phi`, `augment_xb`, `augment_xq` (sotasum/mips.py:55-70, 552-560), the body of
 `Mips.search` (mips.py:382-400), `retriever_metrics` (pretrain.py:69-85) and the doc-score
-statements of `SotasumEncoder.forward` (retriever_generator.py:158-172, 188-192), executes
+statements of `SotasumEncoder.forward` (retriever_generator.py:158-172, 188-192) and the
+generation / copy mixture statements (retriever_generator.py:391-404), executes
 them on seeded inputs and commits the results under tests/golden/. tests/test_oracle.py checks
 every function below against those fixtures. The faiss-cpu 1.7.4 kernels behind
 `faiss_index.search` are a third-party wheel that is not vendored in /root/reference and not
