@@ -37,10 +37,8 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
     override = os.environ.get("MIPS_B200_LIB")   # developer A/B runs: another build of the same ABI
-    if override:
-        path = Path(override)
+    path = Path(override) if override else _build.build()
     L = C.CDLL(str(path))
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     sig = {
