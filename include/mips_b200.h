@@ -34,7 +34,8 @@ typedef struct mips_index_s* mips_handle;
 #define MIPS_METRIC_L2 1
 
 /* Storage / arithmetic type of the bank shard in HBM. */
-#define MIPS_DTYPE_F32 0   /* fp32 rows, exact fp32 FMA search (SIMT)              */
+#define MIPS_DTYPE_F32 0   /* fp32 rows (+ a bf16 shadow): EXACT fp32 search — tcgen05 filter over the shadow,
+                              fp32 re-rank and certificate (MIPS_ALGO_TCX), SIMT fp32 FMA kernel as fallback */
 #define MIPS_DTYPE_BF16 1  /* bf16 rows, tcgen05 tensor-core search, fp32 accumulate */
 
 /* Search kernel selection (testing / bisection; AUTO is what the product uses). */
@@ -60,6 +61,7 @@ typedef struct mips_index_s* mips_handle;
 #define MIPS_E_CUDA -2     /* CUDA runtime or driver error    */
 #define MIPS_E_NOMEM -3    /* allocation failed               */
 #define MIPS_E_UNSUPPORTED -4
+#define MIPS_E_NCCL -5     /* NCCL missing or a collective failed */
 
 #define MIPS_MAX_K 64      /* per-pass top-k capacity of the search kernels */
 
@@ -70,8 +72,11 @@ typedef struct mips_index_s* mips_handle;
  * capacity_rows > 0 pre-sizes the HBM shard (no regrowth while ntotal <= capacity). */
 int mips_create(mips_handle* out, int d, int metric, int dtype, int device, int64_t capacity_rows);
 int mips_destroy(mips_handle h);
-/* faiss Index.reset(): drop all rows, keep the allocation. */
+/* faiss Index.reset(): drop all rows, keep the allocation. mips_reset waits for the device first (searches
+ * of this index still in flight on any stream finish before its statistics are cleared); mips_reset_async
+ * is ordered on `stream` only (the double-buffered refresh resets the back shard on its side stream). */
 int mips_reset(mips_handle h);
+int mips_reset_async(mips_handle h, void* stream);
 int64_t mips_ntotal(mips_handle h);
 /* rows the HBM shard can hold without reallocating (double-buffered refresh reuses allocations) */
 int64_t mips_capacity(mips_handle h);
@@ -160,7 +165,8 @@ int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normal
 const char* mips_last_error(void);
 /* Number of kernels this library has launched so far in this process (bench gpu_launches). */
 int64_t mips_launch_count(void);
-/* Name of the search kernel the last mips_search_local call used ("tc" / "simt"). */
+/* Name of the search path the last mips_search_local call used: "tc2" (CTA-pair tcgen05), "tc" / "tc128"
+ * (1-CTA tcgen05), "tcx" (exact fp32: tcgen05 filter + re-rank + certificate), "simt", or "none". */
 const char* mips_last_algo(mips_handle h);
 /* MIPS_ALGO_TCX statistics: queries (since the last reset) whose exactness certificate failed and
  * that were recomputed by the SIMT kernel. Sync. */
@@ -221,7 +227,12 @@ int mips_gather_tokens(const int32_t* store_ids, const int32_t* store_len, int64
  *       n_peers pointers to this rank's [nq, k] region on each rank, itself included) and whose
  *       completion is signalled on peer_flags[g]; bf16 / SIMT single-chunk searches only
  *   mips_merge_xchg : mips_merge_packed over my_buf = [n_ranks, nq, k_in] records once my_flags[0..n_ranks)
- *       all read `seq` (bounded wait, then the kernel traps) */
+ *       all read `seq`. my_flags is a block of 64 uint32: [0, 32) arrival flags, word MIPS_XCHG_TIMEOUT_WORD
+ *       the time-out flag. The wait is bounded in wall time (MIPS_XCHG_TIMEOUT_S, default 120 s); when it
+ *       expires the affected queries return ids -1 and the time-out flag receives `seq` — the context stays
+ *       usable and the caller falls back to the NCCL exchange
+ *   mips_xchg_timeout_seq : read that flag (0 = no search timed out so far). Sync. */
+#define MIPS_XCHG_TIMEOUT_WORD 32
 int mips_xchg_alloc(int device, int64_t bytes, void** ptr, void* handle64);
 int mips_xchg_open(int device, const void* handle64, void** ptr);
 int mips_xchg_close(int device, void* ptr);
@@ -233,6 +244,46 @@ int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, u
                     int metric, int out_mode, float phi, const float* q_norm2, const int64_t* ignore_ids, float* D,
                     int64_t* I, float* cosine, float* doc_prob, float beta, float beta_bias, float* memory_bias,
                     int mem_len, void* stream);
+int mips_xchg_timeout_seq(int device, const uint32_t* my_flags, uint32_t* out_seq);
+
+/* ---- cross-GPU step through NCCL (K3) --------------------------------------------------------- */
+
+/* The reference never shards (rank 0 builds, every rank loads a full CPU replica: lightning_model.py:168-180);
+ * here the bank is row-sharded with the partition of encode_text2 (sotasum/mips.py:226-230) and each search
+ * combines the per-rank lists with ONE collective on the caller's stream. libnccl.so.2 is
+ * bound at run time (the copy the process already loaded, e.g. the one bundled with the host's tensor
+ * framework; else the system one; MIPS_NCCL_LIB
+ * overrides) — `nccl_comm` is an ncclComm_t passed as void*, either created by mips_nccl_comm_init or any
+ * communicator of the SAME libnccl the host already owns.
+ *   mips_nccl_version     : NCCL_VERSION_CODE of the bound library, -1 when NCCL is unavailable
+ *   mips_nccl_unique_id   : ncclGetUniqueId into id128 (128 bytes) — rank 0, then broadcast by the host
+ *   mips_nccl_comm_init   : ncclCommInitRank on `device` (collective over the n_ranks processes)
+ *   mips_allgather_topk   : ncclAllGather of this rank's [nq, k] 16-byte records -> [n_ranks, nq, k]
+ *   mips_search_sharded   : the whole step, queries REPLICATED on every rank (same q everywhere):
+ *                           query prep + K1 + local merge + all-gather + final merge with the fused doc-score
+ *                           outputs of mips_merge. Every launch goes to `stream`, nothing synchronises, scratch is
+ *                           owned by the handle and stable after the first call: the call can be captured in a
+ *                           CUDA graph (cudaStreamBeginCapture ... EndCapture) and replayed.
+ *   mips_search_sharded_dp: the data-parallel TRAINING step — each rank has its OWN nq_local queries, as every
+ *                           DDP rank calls self.mips(queries=...) with its own batch (retriever_generator.py:143-153
+ *                           driven per rank by lightning_model.py:188-216): all-gather the queries (and ignored
+ *                           ids) -> one local search of n_ranks * nq_local queries -> all-to-all of the records
+ *                           (ncclSend/ncclRecv group) -> each rank merges its own nq_local queries. nq_local and
+ *                           "ignore_local is NULL" must agree across ranks. Outputs are [nq_local, ...]. */
+int mips_nccl_version(void);
+int mips_nccl_unique_id(void* id128);
+int mips_nccl_comm_init(void** comm, int n_ranks, int rank, const void* id128, int device);
+int mips_nccl_comm_destroy(void* comm);
+int mips_allgather_topk(mips_handle h, void* nccl_comm, const void* local_packed, void* gathered_packed, int nq, int k,
+                        void* stream);
+int mips_search_sharded(mips_handle h, void* nccl_comm, int n_ranks, const float* q, int nq, int k, int q_normalize,
+                        const int64_t* ignore_ids, int64_t id_offset, int algo, int out_mode, float* D, int64_t* I,
+                        float* cosine, float* doc_prob, float beta, float beta_bias, float* memory_bias, int mem_len,
+                        void* stream);
+int mips_search_sharded_dp(mips_handle h, void* nccl_comm, int n_ranks, int rank, const float* q_local, int nq_local,
+                           int k, int q_normalize, const int64_t* ignore_local, int64_t id_offset, int algo,
+                           int out_mode, float* D, int64_t* I, float* cosine, float* doc_prob, float beta,
+                           float beta_bias, float* memory_bias, int mem_len, void* stream);
 
 /* ---- generation / copy mixture (next row N3, forward) --------------------------------------- */
 

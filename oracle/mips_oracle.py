@@ -123,6 +123,37 @@ def flat_search(xb: np.ndarray, xq: np.ndarray, k: int, metric_type: int = METRI
     return D.astype(np.float32), best_i
 
 
+def merge_topk_pair(a, b, k: int):
+    """Merge two (D, I) top-k results of disjoint row sets (IP: descending) by (score desc, id asc)."""
+    cat_s = np.concatenate([a[0], b[0]], axis=1)
+    cat_i = np.concatenate([a[1], b[1]], axis=1)
+    order = np.lexsort((cat_i, -cat_s), axis=1)[:, :k]
+    return np.take_along_axis(cat_s, order, axis=1), np.take_along_axis(cat_i, order, axis=1)
+
+
+def flat_search_chunked(xb: np.ndarray, xq: np.ndarray, k: int, chunk_rows: int = 1_000_000):
+    """The reference's CPU search path at full speed on all host threads, inner-product metric: what the flat
+    faiss-cpu index behind `Mips.search` (mips.py:383-386) computes — sgemm of the query batch against a block
+    of bank rows, the k best of each block, a running merge — spelled with the torch idiom the reference itself
+    uses for brute-force scoring (`torch.topk(q @ x.T, k)`, retriever_lightning.py:304-305). Same result as
+    `flat_search` (checked in tests/test_oracle.py); this is the leg bench.py times as the CPU baseline."""
+    import torch
+    tq = torch.from_numpy(np.ascontiguousarray(xq, dtype=np.float32))
+    n = xb.shape[0]
+    best = None
+    for s in range(0, n, chunk_rows):
+        blk = torch.from_numpy(xb[s:s + chunk_rows])
+        v, i = (tq @ blk.T).topk(min(k, blk.shape[0]), dim=1)
+        cur = (v.numpy(), i.numpy().astype(np.int64) + s)
+        best = cur if best is None else merge_topk_pair(best, cur, k)
+    D, I = best
+    if D.shape[1] < k:
+        pad = k - D.shape[1]
+        D = np.concatenate([D, np.full((D.shape[0], pad), -np.inf, dtype=np.float32)], axis=1)
+        I = np.concatenate([I, np.full((I.shape[0], pad), -1, dtype=np.int64)], axis=1)
+    return D.astype(np.float32), I
+
+
 def mips_search(search_fn, queries: np.ndarray, ignore_indexes=None, k: int = 10):
     """Mips.search, mips.py:382-400: fetch k (or k+1 with an ignore list), drop the hit whose id
     equals ignore_indexes[j], keep the first k. Returns numpy arrays without the filter and

@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
         "mips_create": (i32, [C.POINTER(vp), i32, i32, i32, i32, i64]),
         "mips_destroy": (i32, [vp]),
         "mips_reset": (i32, [vp]),
+        "mips_reset_async": (i32, [vp, vp]),
         "mips_ntotal": (i64, [vp]),
         "mips_capacity": (i64, [vp]),
         "mips_dim": (i32, [vp]),
@@ -74,6 +75,16 @@ def lib() -> C.CDLL:
         "mips_search_local_xchg": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, i32, C.c_uint32, vp, vp]),
         "mips_merge_xchg": (i32, [vp, vp, i32, C.c_uint32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, f32,
                                   f32, vp, i32, vp]),
+        "mips_xchg_timeout_seq": (i32, [i32, vp, C.POINTER(C.c_uint32)]),
+        "mips_nccl_version": (i32, []),
+        "mips_nccl_unique_id": (i32, [vp]),
+        "mips_nccl_comm_init": (i32, [C.POINTER(vp), i32, i32, vp, i32]),
+        "mips_nccl_comm_destroy": (i32, [vp]),
+        "mips_allgather_topk": (i32, [vp, vp, vp, vp, i32, i32, vp]),
+        "mips_search_sharded": (i32, [vp, vp, i32, vp, i32, i32, i32, vp, i64, i32, i32, vp, vp, vp, vp, f32, f32, vp,
+                                      i32, vp]),
+        "mips_search_sharded_dp": (i32, [vp, vp, i32, i32, vp, i32, i32, i32, vp, i64, i32, i32, vp, vp, vp, vp, f32,
+                                         f32, vp, i32, vp]),
         "mips_gather_rows": (i32, [vp, vp, i64, i64, vp, vp]),
         "mips_gather_tokens": (i32, [vp, vp, i64, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
         "mips_copy_mixture": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, f32, vp, vp]),

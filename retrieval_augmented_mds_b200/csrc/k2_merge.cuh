@@ -38,7 +38,14 @@ struct XchgIn {
   const uint32_t* flags;     // [n_ranks] arrival flags in THIS rank's buffer
   uint32_t seq;
   int n_ranks;               // 0: no exchange
+  uint32_t* timeout_flag;    // receives `seq` when a peer's list did not arrive in time (host polls it)
+  unsigned long long timeout_ns;
 };
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     const int* __restrict__ q_active = nullptr,   // only these queries are merged (others keep their outputs)
     int stage_cap = 0,                            // LOCAL: shared-memory staging entries per warp (dynamic smem)
     XchgOut xo = XchgOut{nullptr, nullptr, nullptr, 0u, 0},   // LOCAL: publish to the peers
-    XchgIn xi = XchgIn{nullptr, 0u, 0}) {                     // FINAL: wait for the peers
+    XchgIn xi = XchgIn{nullptr, 0u, 0, nullptr, 0ull}) {     // FINAL: wait for the peers
   // 2 * MIPS_MAX_K: the candidate merge of the exact fp32 search keeps up to 128 entries per query
   __shared__ float s_key[4][2 * MIPS_MAX_K];
   __shared__ float s_xn2[4][2 * MIPS_MAX_K];
@@ -85,16 +92,35 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
   if (q >= nq) return;
   if (q_active && !q_active[q]) return;
   if (!LOCAL && xi.n_ranks > 0) {
-    // every rank's list of this search has landed in this rank's buffer (bounded wait: a missing peer
-    // is a launch failure, not a hang)
+    // every rank's list of this search has landed in this rank's buffer. The wait is bounded in wall time
+    // (ordinary rank skew — a checkpoint, a data-loader stall — is minutes at worst); when it expires the
+    // context stays healthy: the query returns "no result" (ids -1) and the time-out flag tells the host,
+    // which falls back to the NCCL exchange (ShardedFlatIndex.check_exchange)
+    bool lost = false;
     if (lane < xi.n_ranks) {
-      unsigned long long spins = 0;
+      const unsigned long long t0 = global_timer_ns();
       while (ld_acquire_sys(xi.flags + lane) != xi.seq) {
         __nanosleep(64);
-        if (++spins > (1ull << 27)) __trap();
+        if (global_timer_ns() - t0 > xi.timeout_ns) {
+          lost = true;
+          break;
+        }
       }
     }
-    __syncwarp();
+    lost = __any_sync(0xffffffffu, lost);
+    if (lost) {
+      if (lane == 0 && xi.timeout_flag) atomicExch(xi.timeout_flag, xi.seq);
+      for (int j = lane; j < k_out; j += 32) {
+        const size_t o = static_cast<size_t>(q) * k_out + j;
+        out_ids[o] = -1;
+        out_key[o] = (out_mode == MIPS_OUT_IP) ? -CUDART_INF_F : CUDART_INF_F;
+        if (cosine) cosine[o] = 0.f;
+        if (doc_prob) doc_prob[o] = 0.f;
+      }
+      if (memory_bias)
+        for (int t = lane; t < k_out * mem_len; t += 32) memory_bias[static_cast<size_t>(q) * k_out * mem_len + t] = 0.f;
+      return;
+    }
   }
 
   const int32_t* ids32 = static_cast<const int32_t*>(cand_ids_v);

@@ -24,6 +24,7 @@
 #include "k5_gather.cuh"
 #include "k6_mixture.cuh"
 #include "mips_b200.h"
+#include "nccl_dl.h"
 
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -99,6 +100,12 @@ struct mips_index_s {
   int64_t fallback_queries = 0;                             // statistics of the last search (host, lazily synced)
   int* fb_count_dev = nullptr;
   float* stage_x = nullptr;    size_t stage_x_bytes = 0;
+  // sharded step (K3): this rank's packed list, the gathered lists, |q|^2, and (DP variant) the gathered queries
+  void* sh_local = nullptr;    size_t sh_local_bytes = 0;
+  void* sh_gath = nullptr;     size_t sh_gath_bytes = 0;
+  float* sh_qn2 = nullptr;     size_t sh_qn2_bytes = 0;
+  float* dp_q = nullptr;       size_t dp_q_bytes = 0;
+  int64_t* dp_ign = nullptr;   size_t dp_ign_bytes = 0;
   // host-call scratch
   float* hq = nullptr;         size_t hq_bytes = 0;
   int64_t* hign = nullptr;     size_t hign_bytes = 0;
@@ -137,7 +144,12 @@ static encode_tiled_fn get_encode_fn() {
 template <typename P>
 static int grow(P** ptr, size_t* cur, size_t need) {
   if (need <= *cur) return 0;
-  if (*ptr) cudaFree(*ptr);
+  if (*ptr) {
+    // a search enqueued earlier (on any stream of this device) may still use the old scratch: growth is
+    // rare (sizes are stable after warm-up), so it simply waits for the device before freeing
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(*ptr);
+  }
   *ptr = nullptr;
   *cur = 0;
   size_t bytes = std::max(need, static_cast<size_t>(256));
@@ -188,28 +200,32 @@ static int encode_query_tmap(mips_index_s* h, const void* q_bf16, int rows) {
 }
 
 // (re)allocate the shard to hold at least `rows`; preserves existing rows.
+namespace {
+struct DevBufGuard {   // frees what ensure_capacity allocated unless it is released to the index
+  void* p[3] = {nullptr, nullptr, nullptr};
+  ~DevBufGuard() {
+    for (void* q : p)
+      if (q) cudaFree(q);
+  }
+  void release() { p[0] = p[1] = p[2] = nullptr; }
+};
+}  // namespace
+
 static int ensure_capacity(mips_index_s* h, int64_t rows, cudaStream_t st) {
   if (rows <= h->capacity) return 0;
   int64_t cap = std::max<int64_t>(rows, h->capacity * 2);
   cap = std::max<int64_t>(round_up_l(cap, kRowAlign), 1024);
-  void* nb = nullptr;
-  float* nn = nullptr;
+  DevBufGuard g;
   const size_t row_bytes = static_cast<size_t>(h->d_pad) * elem_bytes(h);
-  CUDA_TRY(cudaMalloc(&nb, static_cast<size_t>(cap) * row_bytes));
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&nn), static_cast<size_t>(cap) * sizeof(float));
-  if (e != cudaSuccess) {
-    cudaFree(nb);
-    return set_err(MIPS_E_NOMEM, "cudaMalloc norm array: %s", cudaGetErrorString(e));
-  }
-  __nv_bfloat16* ns = nullptr;
   const size_t srow_bytes = static_cast<size_t>(h->d_pad) * 2;
-  if (h->dtype == MIPS_DTYPE_F32 && h->d_pad <= tc2::MAX_KCH * tc2::KCH) {
-    e = cudaMalloc(reinterpret_cast<void**>(&ns), static_cast<size_t>(cap) * srow_bytes);
-    if (e != cudaSuccess) {
-      cudaFree(nb);
-      cudaFree(nn);
-      return set_err(MIPS_E_NOMEM, "cudaMalloc bf16 shadow: %s", cudaGetErrorString(e));
-    }
+  CUDA_TRY(cudaMalloc(&g.p[0], static_cast<size_t>(cap) * row_bytes));
+  CUDA_TRY(cudaMalloc(&g.p[1], static_cast<size_t>(cap) * sizeof(float)));
+  const bool want_shadow = h->dtype == MIPS_DTYPE_F32 && h->d_pad <= tc2::MAX_KCH * tc2::KCH;
+  if (want_shadow) CUDA_TRY(cudaMalloc(&g.p[2], static_cast<size_t>(cap) * srow_bytes));
+  void* nb = g.p[0];
+  float* nn = static_cast<float*>(g.p[1]);
+  __nv_bfloat16* ns = static_cast<__nv_bfloat16*>(g.p[2]);
+  if (ns) {
     if (h->ntotal > 0 && h->shadow)
       CUDA_TRY(cudaMemcpyAsync(ns, h->shadow, static_cast<size_t>(h->ntotal) * srow_bytes, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemsetAsync(reinterpret_cast<uint8_t*>(ns) + static_cast<size_t>(h->ntotal) * srow_bytes, 0,
@@ -225,7 +241,10 @@ static int ensure_capacity(mips_index_s* h, int64_t rows, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(static_cast<uint8_t*>(nb) + static_cast<size_t>(h->ntotal) * row_bytes, 0,
                            static_cast<size_t>(cap - h->ntotal) * row_bytes, st));
   CUDA_TRY(cudaMemsetAsync(nn + h->ntotal, 0, static_cast<size_t>(cap - h->ntotal) * sizeof(float), st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  // the old allocation may still be read by searches on other streams of this device: a reallocation
+  // waits for all of them (rare: growth is geometric, or never with capacity_rows)
+  CUDA_TRY(cudaDeviceSynchronize());
+  g.release();
   if (h->bank) cudaFree(h->bank);
   if (h->norm2) cudaFree(h->norm2);
   if (h->shadow) cudaFree(h->shadow);
@@ -318,7 +337,7 @@ int mips_destroy(mips_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* dev[] = {h->bank, h->norm2, h->max_norm2_bits, h->q_prep, h->q_norm2, h->part_key,
-                 h->part_ids, h->ign_local, h->pace, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->hq, h->hign, h->hkey, h->hids,
+                 h->part_ids, h->ign_local, h->pace, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->sh_local, h->sh_gath, h->sh_qn2, h->dp_q, h->dp_ign, h->hq, h->hign, h->hkey, h->hids,
                  h->hxn2, h->hqn2, h->hD, h->hI};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -331,13 +350,22 @@ int mips_destroy(mips_handle h) {
   return 0;
 }
 
-int mips_reset(mips_handle h) {
+int mips_reset_async(mips_handle h, void* stream) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
   h->ntotal = 0;
   h->phi = 0.f;
-  CUDA_TRY(cudaMemset(h->max_norm2_bits, 0, 8 * sizeof(unsigned int)));
+  // stream ordered: searches enqueued earlier on `stream` still see their certificate maxima / counters
+  CUDA_TRY(cudaMemsetAsync(h->max_norm2_bits, 0, 8 * sizeof(unsigned int), static_cast<cudaStream_t>(stream)));
   return 0;
+}
+
+int mips_reset(mips_handle h) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // no stream to order against: wait for whatever is still searching this index (any stream of the device)
+  CUDA_TRY(cudaDeviceSynchronize());
+  return mips_reset_async(h, nullptr);
 }
 
 int64_t mips_ntotal(mips_handle h) { return h ? h->ntotal : -1; }
@@ -1108,13 +1136,158 @@ int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, u
   if ((out_mode != MIPS_OUT_IP || cosine || doc_prob || memory_bias) && !q_norm2)
     return set_err(MIPS_E_INVALID, "q_norm2 required for L2 / cosine outputs");
   if (memory_bias && mem_len < 1) return set_err(MIPS_E_INVALID, "mem_len must be >= 1");
+  static const int xchg_timeout_s = env_int("MIPS_XCHG_TIMEOUT_S", 120);
   merge_topk_kernel<false><<<(nq + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       nullptr, nullptr, nullptr, nullptr, n_ranks, nq, k_in, k_out, 0, ignore_ids, metric, out_mode, phi, q_norm2, D, I,
       nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, static_cast<const PackedCand*>(my_buf), nullptr,
-      nullptr, 0, XchgOut{nullptr, nullptr, nullptr, 0u, 0}, XchgIn{my_flags, seq, n_ranks});
+      nullptr, 0, XchgOut{nullptr, nullptr, nullptr, 0u, 0},
+      XchgIn{my_flags, seq, n_ranks, const_cast<uint32_t*>(my_flags) + MIPS_XCHG_TIMEOUT_WORD,
+             static_cast<unsigned long long>(std::max(1, xchg_timeout_s)) * 1000000000ull});
   LAUNCH_CHECK("merge_topk_kernel<final, peer exchange>");
   return 0;
 }
+
+int mips_xchg_timeout_seq(int device, const uint32_t* my_flags, uint32_t* out_seq) {
+  if (!my_flags || !out_seq) return set_err(MIPS_E_INVALID, "bad arguments");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMemcpy(out_seq, my_flags + MIPS_XCHG_TIMEOUT_WORD, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ K3 (NCCL)
+#define NCCL_TRY(expr)                                                                              \
+  do {                                                                                              \
+    int _r = (expr);                                                                                \
+    if (_r != 0) return set_err(MIPS_E_NCCL, "%s: %s", #expr, nc->GetErrorString(_r));              \
+  } while (0)
+
+int mips_nccl_version(void) {
+  const nccl_dl::Api* nc = nccl_dl::api();
+  int v = 0;
+  if (!nc || nc->GetVersion(&v) != 0) return -1;
+  return v;
+}
+
+int mips_nccl_unique_id(void* id128) {
+  if (!id128) return set_err(MIPS_E_INVALID, "id128 is NULL");
+  const nccl_dl::Api* nc = nccl_dl::api();
+  if (!nc) return set_err(MIPS_E_NCCL, "%s", nccl_dl::why_unavailable());
+  nccl_dl::UniqueId id;
+  NCCL_TRY(nc->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int mips_nccl_comm_init(void** comm, int n_ranks, int rank, const void* id128, int device) {
+  if (!comm || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_err(MIPS_E_INVALID, "bad communicator arguments");
+  *comm = nullptr;
+  const nccl_dl::Api* nc = nccl_dl::api();
+  if (!nc) return set_err(MIPS_E_NCCL, "%s", nccl_dl::why_unavailable());
+  CUDA_TRY(cudaSetDevice(device));
+  nccl_dl::UniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  nccl_dl::Comm c = nullptr;
+  NCCL_TRY(nc->CommInitRank(&c, n_ranks, id, rank));
+  *comm = c;
+  return 0;
+}
+
+int mips_nccl_comm_destroy(void* comm) {
+  if (!comm) return 0;
+  const nccl_dl::Api* nc = nccl_dl::api();
+  if (!nc) return set_err(MIPS_E_NCCL, "%s", nccl_dl::why_unavailable());
+  NCCL_TRY(nc->CommDestroy(comm));
+  return 0;
+}
+
+int mips_allgather_topk(mips_handle h, void* nccl_comm, const void* local_packed, void* gathered_packed, int nq, int k,
+                        void* stream) {
+  if (!h || !nccl_comm) return set_err(MIPS_E_INVALID, "null handle / communicator");
+  if (nq < 0 || k < 1 || (nq > 0 && (!local_packed || !gathered_packed))) return set_err(MIPS_E_INVALID, "bad buffers");
+  if (nq == 0) return 0;
+  const nccl_dl::Api* nc = nccl_dl::api();
+  if (!nc) return set_err(MIPS_E_NCCL, "%s", nccl_dl::why_unavailable());
+  CUDA_TRY(cudaSetDevice(h->device));
+  NCCL_TRY(nc->AllGather(local_packed, gathered_packed, static_cast<size_t>(nq) * k * sizeof(PackedCand), nccl_dl::kUint8,
+                         nccl_comm, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int mips_search_sharded(mips_handle h, void* nccl_comm, int n_ranks, const float* q, int nq, int k, int q_normalize,
+                        const int64_t* ignore_ids, int64_t id_offset, int algo, int out_mode, float* D, int64_t* I,
+                        float* cosine, float* doc_prob, float beta, float beta_bias, float* memory_bias, int mem_len,
+                        void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (n_ranks < 1 || (n_ranks > 1 && !nccl_comm)) return set_err(MIPS_E_INVALID, "n_ranks > 1 needs a communicator");
+  if (nq < 0 || (nq > 0 && (!q || !D || !I))) return set_err(MIPS_E_INVALID, "bad q / outputs");
+  if (nq == 0) return 0;
+  int rc;
+  const size_t rec = static_cast<size_t>(nq) * k * sizeof(PackedCand);
+  if ((rc = grow(&h->sh_local, &h->sh_local_bytes, rec))) return rc;
+  if ((rc = grow(&h->sh_qn2, &h->sh_qn2_bytes, static_cast<size_t>(nq) * sizeof(float)))) return rc;
+  if (n_ranks > 1 && (rc = grow(&h->sh_gath, &h->sh_gath_bytes, rec * n_ranks))) return rc;
+  rc = mips_search_local_packed(h, q, nq, k, q_normalize, ignore_ids, id_offset, algo, h->sh_local, h->sh_qn2, stream);
+  if (rc) return rc;
+  const void* cand = h->sh_local;
+  if (n_ranks > 1) {
+    if ((rc = mips_allgather_topk(h, nccl_comm, h->sh_local, h->sh_gath, nq, k, stream))) return rc;
+    cand = h->sh_gath;
+  }
+  return mips_merge_packed(cand, n_ranks, nq, k, k, h->metric, out_mode, h->phi, h->sh_qn2, nullptr, D, I, cosine,
+                           doc_prob, beta, beta_bias, memory_bias, mem_len, stream);
+}
+
+int mips_search_sharded_dp(mips_handle h, void* nccl_comm, int n_ranks, int rank, const float* q_local, int nq_local,
+                           int k, int q_normalize, const int64_t* ignore_local, int64_t id_offset, int algo,
+                           int out_mode, float* D, int64_t* I, float* cosine, float* doc_prob, float beta,
+                           float beta_bias, float* memory_bias, int mem_len, void* stream) {
+  if (!h) return set_err(MIPS_E_INVALID, "null handle");
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks || (n_ranks > 1 && !nccl_comm))
+    return set_err(MIPS_E_INVALID, "bad rank / n_ranks / communicator");
+  if (nq_local < 0 || (nq_local > 0 && (!q_local || !D || !I))) return set_err(MIPS_E_INVALID, "bad q / outputs");
+  if (nq_local == 0) return 0;   // every rank passes the same nq_local: nobody enters a collective
+  if (n_ranks == 1)
+    return mips_search_sharded(h, nullptr, 1, q_local, nq_local, k, q_normalize, ignore_local, id_offset, algo, out_mode,
+                               D, I, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, stream);
+  const nccl_dl::Api* nc = nccl_dl::api();
+  if (!nc) return set_err(MIPS_E_NCCL, "%s", nccl_dl::why_unavailable());
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nq_all = nq_local * n_ranks;
+  const size_t rec_local = static_cast<size_t>(nq_local) * k * sizeof(PackedCand);   // one rank's queries
+  int rc;
+  if ((rc = grow(&h->dp_q, &h->dp_q_bytes, static_cast<size_t>(nq_all) * h->d * sizeof(float)))) return rc;
+  if ((rc = grow(&h->sh_local, &h->sh_local_bytes, rec_local * n_ranks))) return rc;
+  if ((rc = grow(&h->sh_gath, &h->sh_gath_bytes, rec_local * n_ranks))) return rc;
+  if ((rc = grow(&h->sh_qn2, &h->sh_qn2_bytes, static_cast<size_t>(nq_all) * sizeof(float)))) return rc;
+  // 1. every rank learns every rank's queries (and ignored ids): [G * B, d], rank major
+  NCCL_TRY(nc->AllGather(q_local, h->dp_q, static_cast<size_t>(nq_local) * h->d, nccl_dl::kFloat32, nccl_comm, st));
+  const int64_t* ign_all = nullptr;
+  if (ignore_local) {
+    if ((rc = grow(&h->dp_ign, &h->dp_ign_bytes, static_cast<size_t>(nq_all) * sizeof(int64_t)))) return rc;
+    NCCL_TRY(nc->AllGather(ignore_local, h->dp_ign, static_cast<size_t>(nq_local), nccl_dl::kInt64, nccl_comm, st));
+    ign_all = h->dp_ign;
+  }
+  // 2. one local search of all G * B queries over this rank's shard
+  rc = mips_search_local_packed(h, h->dp_q, nq_all, k, q_normalize, ign_all, id_offset, algo, h->sh_local, h->sh_qn2, stream);
+  if (rc) return rc;
+  // 3. all-to-all of the 16-byte records: rank r receives, from every shard, the lists of ITS B queries
+  NCCL_TRY(nc->GroupStart());
+  for (int g = 0; g < n_ranks; ++g) {
+    int r1 = nc->Send(static_cast<const uint8_t*>(h->sh_local) + rec_local * g, rec_local, nccl_dl::kUint8, g, nccl_comm, st);
+    int r2 = r1 ? r1 : nc->Recv(static_cast<uint8_t*>(h->sh_gath) + rec_local * g, rec_local, nccl_dl::kUint8, g, nccl_comm, st);
+    if (r2) {
+      nc->GroupEnd();
+      return set_err(MIPS_E_NCCL, "ncclSend/ncclRecv: %s", nc->GetErrorString(r2));
+    }
+  }
+  NCCL_TRY(nc->GroupEnd());
+  // 4. each rank merges the G lists of its own queries (+ the fused doc-score outputs)
+  return mips_merge_packed(h->sh_gath, n_ranks, nq_local, k, k, h->metric, out_mode, h->phi,
+                           h->sh_qn2 + static_cast<size_t>(rank) * nq_local, nullptr, D, I, cosine, doc_prob, beta,
+                           beta_bias, memory_bias, mem_len, stream);
+}
+#undef NCCL_TRY
 
 // ------------------------------------------------------------------------------------------ mixture
 int mips_copy_mixture(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
@@ -1126,12 +1299,15 @@ int mips_copy_mixture(const float* logits, const float* gen_gate, const float* c
   if (V > mix::MAX_V)
     return set_err(MIPS_E_UNSUPPORTED, "vocabulary of %d does not fit one CTA's shared memory (max %d)", V, mix::MAX_V);
   if (n_rows > 0x7fffffff) return set_err(MIPS_E_INVALID, "too many rows");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  mix::MAX_HALF * static_cast<int>(sizeof(float))));
-    attr_set = true;
-  }
+  // the opt-in is per DEVICE (and this entry point has no handle): run on the device that owns `logits`
+  // and set the attribute there on every call (a few hundred ns on the host, no device work)
+  cudaPointerAttributes pa;
+  CUDA_TRY(cudaPointerGetAttributes(&pa, logits));
+  if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged)
+    return set_err(MIPS_E_INVALID, "logits must be device memory");
+  CUDA_TRY(cudaSetDevice(pa.device));
+  CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                mix::MAX_HALF * static_cast<int>(sizeof(float))));
   if (n_rows > 0x3fffffff) return set_err(MIPS_E_INVALID, "too many rows");
   mix::copy_mixture_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS, static_cast<size_t>((V + 1) / 2) * sizeof(float),
                              static_cast<cudaStream_t>(stream)>>>(logits, gen_gate, copy_probs, copy_seq,

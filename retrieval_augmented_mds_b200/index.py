@@ -85,7 +85,9 @@ class B200FlatIndex:
         return int(self._L.mips_capacity(self._h))
 
     def reset(self) -> None:
-        check(self._L.mips_reset(self._h))
+        """faiss Index.reset(), ordered on the current torch stream of the index's device."""
+        with torch.cuda.device(self.device):
+            check(self._L.mips_reset_async(self._h, self._stream()))
 
     def train(self, x=None) -> None:  # flat index: nothing to train (datasets calls it when train_size is set)
         return None
@@ -302,6 +304,16 @@ class B200FlatIndex:
         return self.merge(key.unsqueeze(0), ids.unsqueeze(0), xn2.unsqueeze(0), qn2, k, want=want,
                           out_mode=out_mode, mem_len=L, beta=beta, beta_bias=beta_bias)
 
+    def capture(self, nq: int, k: int, with_ignore: bool = False, want: Iterable[str] = ("scores", "ids"),
+                L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
+                beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> "GraphedSearch":
+        """Capture query prep -> K1 -> merges (one C-ABI call, mips_search_sharded with one rank) as ONE CUDA
+        graph over static buffers; a replay is a single launch."""
+        k = self._check_k(k)
+        return GraphedSearch(self, int(nq), k, with_ignore, want, L,
+                             lambda xq, ign, out: sharded_step(self, None, 1, 0, False, xq, ign, k, out, L,
+                                                               normalize_queries, out_mode, beta, beta_bias, algo))
+
     # ------------------------------------------------------------------ profiling hooks (bench)
     def set_profiling(self, on: bool) -> None:
         check(self._L.mips_set_profiling(self._h, int(on)))
@@ -317,6 +329,76 @@ class B200FlatIndex:
         """Exact tensor-core search ("tcx", fp32 banks): how many queries failed the exactness
         certificate since the last reset and were recomputed by the exact SIMT kernel."""
         return int(self._L.mips_fallback_queries(self._h, int(reset)))
+
+
+def alloc_outputs(dev, nq: int, k: int, want, L) -> dict:
+    """Output tensors of one search step for the requested `want` set."""
+    want = set(want)
+    unknown = want - {"scores", "ids", "cosine", "doc_prob", "memory_bias"}
+    if unknown:
+        raise ValueError(f"unknown outputs requested: {sorted(unknown)}")
+    out = {"scores": torch.empty((nq, k), dtype=torch.float32, device=dev),
+           "ids": torch.empty((nq, k), dtype=torch.int64, device=dev)}
+    if want & {"cosine", "memory_bias", "doc_prob"}:
+        out["cosine"] = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    if "doc_prob" in want:
+        out["doc_prob"] = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    if "memory_bias" in want:
+        if not L or L < 1:
+            raise ValueError("memory_bias needs L (memory_seq_len) >= 1")
+        out["memory_bias"] = torch.empty((nq, k * int(L)), dtype=torch.float32, device=dev)
+    return out
+
+
+def sharded_step(local: "B200FlatIndex", comm_ptr, world: int, rank: int, dp: bool, xq: torch.Tensor,
+                 ign: Optional[torch.Tensor], k: int, out: dict, L, normalize_queries, out_mode, beta, beta_bias,
+                 algo: str) -> dict:
+    """ONE C-ABI call for a whole search step on the current stream: mips_search_sharded (queries replicated)
+    or mips_search_sharded_dp (every rank its own queries). world == 1 needs no communicator."""
+    lib = _lib.lib()
+    if out_mode is None:
+        out_mode = OUT_IP if local.metric_type == METRIC_INNER_PRODUCT else OUT_L2
+    with torch.cuda.device(local.device):
+        tail = (int(out_mode), _ptr(out["scores"]), _ptr(out["ids"]), _ptr(out.get("cosine")), _ptr(out.get("doc_prob")),
+                float(beta), float(beta_bias), _ptr(out.get("memory_bias")), int(L or 0), local._stream())
+        if dp:
+            check(lib.mips_search_sharded_dp(local._h, comm_ptr, world, rank, _ptr(xq), xq.shape[0], int(k),
+                                             int(normalize_queries), _ptr(ign), local.id_offset, _ALGOS[algo], *tail))
+        else:
+            check(lib.mips_search_sharded(local._h, comm_ptr, world, _ptr(xq), xq.shape[0], int(k),
+                                          int(normalize_queries), _ptr(ign), local.id_offset, _ALGOS[algo], *tail))
+    return out
+
+
+class GraphedSearch:
+    """One CUDA graph holding a whole search step (B200FlatIndex.capture, ShardedFlatIndex.capture). `xq` (and
+    `ignore_ids`) are static input tensors: replay(xq) copies into them (from the device or from pinned host
+    memory) and launches the graph; results land in `.out` (static, overwritten by the next replay)."""
+
+    def __init__(self, local: "B200FlatIndex", nq: int, k: int, with_ignore: bool, want, L, call):
+        dev = local.device
+        self.nq, self.k = nq, k
+        self.xq = torch.zeros((nq, local.d), dtype=torch.float32, device=dev)
+        self.ignore_ids = torch.full((nq,), -1, dtype=torch.int64, device=dev) if with_ignore else None
+        self.out = alloc_outputs(dev, nq, k, want, L)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):             # warm-up: scratch reaches its final size, NCCL connects its peers
+            for _ in range(2):
+                call(self.xq, self.ignore_ids, self.out)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            call(self.xq, self.ignore_ids, self.out)
+
+    def replay(self, xq: Optional[torch.Tensor] = None, ignore_ids: Optional[torch.Tensor] = None) -> dict:
+        if xq is not None:
+            self.xq.copy_(xq, non_blocking=True)
+        if ignore_ids is not None:
+            self.ignore_ids.copy_(ignore_ids, non_blocking=True)
+        self.graph.replay()
+        return self.out
 
 
 def merge_candidates(key: Optional[torch.Tensor], ids: Optional[torch.Tensor], xn2: Optional[torch.Tensor],

@@ -38,6 +38,46 @@ class MipsConfig:
     mips_tmp_folder: str = "./tmp"
     # ours
     bank_dtype: str = "bf16"                   # "bf16" (tcgen05 path) or "fp32" (exact fp32 path)
+    # row-sharded bank only. False (default) = the reference's data-parallel semantics: every rank searches
+    # with its OWN batch (each DDP rank calls self.mips(queries=...), retriever_generator.py:143-153) ->
+    # ShardedFlatIndex.search_dp. True = every rank passes the SAME queries (evaluation / serving): the
+    # cheaper replicated step, ShardedFlatIndex.search.
+    replicated_queries: bool = False
+
+
+@dataclass
+class MipsModelOutput:
+    """The search-result fields of the reference's `MipsModelOutput` (sotasum/mips.py:33-42), same names:
+    `scores` = what `Mips.search` returned (raw index scores), `query_cls` = the queries as searched,
+    `memory_input_ids` / `memory_attention_mask` = the retrieved documents' tokens (mips.py:473-505; here
+    gathered on the device from a MemoryTokenStore), `metrics` = retriever_metrics (mips.py:456-463).
+    `examples` carries text rows in the reference (Arrow lookup, out of scope): here it holds the retrieved
+    ids [B, k], from which the caller's own table gives the rows. `mips_last_hidden_state` /
+    `memory_outputs` are encoder outputs (out of scope) and stay None."""
+    scores: object = None
+    mips_last_hidden_state: object = None
+    memory_outputs: object = None
+    memory_input_ids: object = None
+    memory_attention_mask: object = None
+    metrics: Optional[dict] = None
+    examples: object = None
+    query_cls: object = None
+
+
+@dataclass
+class RGEncoderModelOutput:
+    """The retrieval fields of the reference's `RGEncoderModelOutput` (sotasum/retriever_generator.py:29-42),
+    same names: `mips_scores` = cosine doc scores [B, k] (:158-172), `faiss_scores` = raw index scores (:222),
+    `memory_bias` [B, k*L] (:188-192), `memory_mask` / `copy_sequence` [B, k*L] (:187,193), `query_cls`,
+    `examples` (ids, see MipsModelOutput). The encoder hidden states of the reference class are out of scope."""
+    memory_mask: object = None
+    memory_bias: object = None
+    copy_sequence: object = None
+    mips_scores: object = None
+    examples: object = None
+    faiss_scores: object = None
+    query_cls: object = None
+    doc_prob: object = None            # ours: softmax_j(beta * mips_scores_j + beta_bias), the per-doc factor
 
 
 class Mips:
@@ -109,15 +149,19 @@ class Mips:
         mips.py:226-230). The previous back buffer is reused when it is large enough (no cudaMalloc)."""
         d = d if d is not None else self.index.d
         back = getattr(self, "_back", None)
-        if back is not None and back.d == d and back.capacity >= n_rows_local and back.dtype == self.args.bank_dtype:
-            back.reset()
-        else:
+        reuse = back is not None and back.d == d and back.capacity >= n_rows_local and back.dtype == self.args.bank_dtype
+        if not reuse:
             back = B200FlatIndex(d, METRIC_INNER_PRODUCT, dtype=self.args.bank_dtype, device=self.device,
                                  capacity=max(n_rows_local, 1))
         self._back = back
         if getattr(self, "_refresh_stream", None) is None:
             self._refresh_stream = torch.cuda.Stream(device=back.device)
+        # the back shard was the FRONT shard until the last commit: its reset (stream ordered) must come after
+        # every search already enqueued on the caller's stream
         self._refresh_stream.wait_stream(torch.cuda.current_stream(back.device))
+        if reuse:
+            with torch.cuda.stream(self._refresh_stream):
+                back.reset()
 
     def refresh_add(self, embeddings: torch.Tensor) -> None:
         """One block of freshly encoded rows (CUDA float tensor [n, d]) -> back shard, on the side stream."""
@@ -127,8 +171,13 @@ class Mips:
             if embeddings.shape[0] == 0:
                 return
         fuse_norm = bool(self.normalize and self.metric_type == METRIC_INNER_PRODUCT)
+        # the block was produced by kernels on the caller's stream (the encoder forward): the ingest on the
+        # side stream must not start before they finish
+        self._refresh_stream.wait_stream(torch.cuda.current_stream(self._back.device))
         with torch.cuda.stream(self._refresh_stream):
             self._back.add(embeddings, normalize=fuse_norm)
+        if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda:
+            embeddings.record_stream(self._refresh_stream)      # keep the block alive until K0 has read it
 
     def commit_refresh(self, global_step: int) -> None:
         """Make the back buffer the one searches see (collective when the bank is row-sharded)."""
@@ -137,7 +186,10 @@ class Mips:
         front = self.index
         self.index = back
         if self.group is not None:
+            old = self._sharded
             self._sharded = _sharded.ShardedFlatIndex(back, self.group)
+            if old is not None:
+                self._sharded.adopt(old)            # keep the communicator / exchange buffers: no leak per refresh
             off, self._sharded.counts = _sharded.exchange_offsets(back.ntotal, self.group, back.device)
             back.id_offset = off
             mn2 = _sharded.allreduce_max(back.max_norm2(), self.group, back.device)
@@ -183,8 +235,9 @@ class Mips:
         queries = np.ascontiguousarray(self._strip(np.asarray(queries)), dtype=np.float32)
         out_mode = OUT_AUGL2 if self.metric_type == METRIC_L2 else OUT_IP
         if self._sharded is not None and self._sharded.world > 1:
-            r = self._sharded.search(torch.from_numpy(queries), k, ignore_ids=None if ignore_indexes is None
-                                     else torch.as_tensor(ignore_indexes, dtype=torch.int64), out_mode=out_mode)
+            fn = self._sharded.search if self.args.replicated_queries else self._sharded.search_dp
+            r = fn(torch.from_numpy(queries), k, ignore_ids=None if ignore_indexes is None
+                   else torch.as_tensor(ignore_indexes, dtype=torch.int64), out_mode=out_mode)
             scores, indices = r["scores"].cpu().numpy(), r["ids"].cpu().numpy()
         else:
             ign = None if ignore_indexes is None else np.asarray(ignore_indexes, dtype=np.int64)
@@ -202,12 +255,21 @@ class Mips:
             raise RuntimeError("build_index() or load() first")
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert len(x.shape) == 2
+        index = self.index
         if self.normalize and self.metric_type != METRIC_INNER_PRODUCT:
-            # the stored rows are not unit-norm in this configuration, so the reference's
-            # per-call renormalisation ranks by cosine, which this index does not store
-            raise NotImplementedError("np_search with normalize=True needs the IP metric (unit-norm bank)")
-        r = self.index.search_ex(torch.from_numpy(x), k, normalize_queries=bool(self.normalize),
-                                 want=("scores", "ids", "cosine") if self.normalize else ("scores", "ids"))
+            # normalize with the L2 metric: the stored rows are NOT unit-norm, and the reference's per-call
+            # renormalisation of both sides (mips.py:554-556) ranks by cosine. Do what it does, on the GPU:
+            # a unit-norm copy of the bank (K0 with the fused normalisation), kept until the bank changes.
+            key = (id(index), index.ntotal)
+            if getattr(self, "_unit_bank_key", None) != key:
+                unit = B200FlatIndex(index.d, METRIC_INNER_PRODUCT, dtype=index.dtype, device=index.device,
+                                     capacity=max(index.ntotal, 1))
+                for i in range(0, index.ntotal, 262144):
+                    unit.add(index.reconstruct_n(i, min(262144, index.ntotal - i), as_torch=True), normalize=True)
+                self._unit_bank, self._unit_bank_key = unit, key
+            index = self._unit_bank
+        r = index.search_ex(torch.from_numpy(x), k, normalize_queries=bool(self.normalize),
+                            want=("scores", "ids", "cosine") if self.normalize else ("scores", "ids"))
         scores = r["cosine"] if self.normalize else r["scores"]
         return scores.cpu().numpy(), r["ids"].cpu().numpy()
 
@@ -221,10 +283,65 @@ class Mips:
         want = ["scores", "ids", "cosine", "doc_prob"] + (["memory_bias"] if memory_seq_len else [])
         out_mode = OUT_AUGL2 if self.metric_type == METRIC_L2 else OUT_IP
         norm_q = bool(self.normalize and self.metric_type == METRIC_INNER_PRODUCT)
-        target = self._sharded if (self._sharded is not None and self._sharded.world > 1) else self.index
-        fn = target.search if target is self._sharded else target.search_ex
+        if self._sharded is not None and self._sharded.world > 1:
+            fn = self._sharded.search if self.args.replicated_queries else self._sharded.search_dp
+        else:
+            fn = self.index.search_ex
         return fn(queries, k, ignore_ids=ignore_indexes, want=want, L=memory_seq_len,
                   normalize_queries=norm_q, out_mode=out_mode, beta=beta, beta_bias=beta_bias)
+
+    def forward(self, queries, k: int = 10, ignore_indexes=None, aid=None, aid_counts=None, row_aid=None,
+                token_store=None) -> MipsModelOutput:
+        """The search part of `Mips.forward` (mips.py:402-519) with the reference's output container:
+        prepare the queries (:421), search (:422-426), optional retrieval metrics (:456-463: `aid` [B],
+        `aid_counts` [B] and `row_aid` [N] = the `aid` column of the memory) and the retrieved documents'
+        tokens (:473-505) from a MemoryTokenStore. `queries` float [B, d], numpy like the reference or a CUDA
+        tensor (then nothing leaves the device). Text assembly and the encoders are out of scope."""
+        if self.index is None:
+            raise RuntimeError("build_index() or load() first")
+        dev = self.index.device
+        if isinstance(queries, torch.Tensor):
+            q_dev = queries.detach().to(device=dev, dtype=torch.float32)
+            query_cls = q_dev
+        else:
+            query_cls = np.asarray(queries, dtype=np.float32)
+            q_dev = torch.from_numpy(np.ascontiguousarray(query_cls)).to(dev)
+        r = self.search_device(q_dev, k, ignore_indexes=ignore_indexes)
+        metrics = None
+        if aid is not None and aid_counts is not None and row_aid is not None:
+            m = _index.retriever_metrics(r["ids"], torch.as_tensor(row_aid).to(dev), torch.as_tensor(aid).to(dev),
+                                         torch.as_tensor(aid_counts, dtype=torch.float32).to(dev))
+            metrics = {"recall": m["recall"], "reciprocal_rank": m["reciprocal_rank"],
+                       "average_precision": m["average_precision"]}
+        mem_ids = mem_mask = None
+        if token_store is not None:
+            g = token_store.gather(r["ids"])
+            B, L = r["ids"].shape[0], token_store.seq_len
+            mem_ids = g["memory_input_ids"].view(B, k, L)                 # mips.py:499-505
+            mem_mask = g["memory_attention_mask"].view(B, k, L)
+        return MipsModelOutput(scores=r["scores"], memory_input_ids=mem_ids, memory_attention_mask=mem_mask,
+                               metrics=metrics, examples=r["ids"], query_cls=query_cls)
+
+    def retrieve_for_generator(self, query: torch.Tensor, k: int, ignore_indexes=None, token_store=None,
+                               memory_seq_len: Optional[int] = None, beta: float = 1.0,
+                               beta_bias: float = 0.0) -> RGEncoderModelOutput:
+        """The retrieval block of `SotasumEncoder.forward` (retriever_generator.py:138-193) for a frozen memory
+        encoder, with the reference's field names: `query` is the CLS slice [B, 1, d] or [B, d] ON THE GPU (no
+        `.cpu()` round trip, :143); returns `faiss_scores` (raw search scores, :222), `mips_scores` (cosine,
+        :158-172), `memory_bias` [B, k*L] (:188-192) and, with a MemoryTokenStore, `memory_mask` /
+        `copy_sequence` [B, k*L] (:187,193)."""
+        q = query[:, 0, :] if query.dim() == 3 else query
+        L = token_store.seq_len if token_store is not None else memory_seq_len
+        r = self.search_device(q, k, ignore_indexes=ignore_indexes, memory_seq_len=L, beta=beta, beta_bias=beta_bias)
+        mask = copy_seq = None
+        if token_store is not None:
+            g = token_store.gather(r["ids"])
+            B = r["ids"].shape[0]
+            mask = g["memory_attention_mask"].view(B, -1)
+            copy_seq = g["memory_input_ids"].view(B, -1)
+        return RGEncoderModelOutput(memory_mask=mask, memory_bias=r.get("memory_bias"), copy_sequence=copy_seq,
+                                    mips_scores=r["cosine"], examples=r["ids"], faiss_scores=r["scores"],
+                                    query_cls=q, doc_prob=r["doc_prob"])
 
     # ------------------------------------------------------------------ save / load (mips.py:531-549)
     def _rank_suffix(self) -> str:
@@ -270,10 +387,21 @@ class Mips:
                        "phi": None if self.phi is None else float(self.phi)}, f)
         try:
             import datasets  # optional: the reference's load() also wants the Arrow `embeddings` folder
-            ds = datasets.Dataset.from_dict({self.embeddings_column: np.concatenate(list(blocks())) if n else np.zeros((0, d), np.float32)})
-            ds.save_to_disk(str(self.embeddings_folder) + sfx)
         except ImportError:
-            pass
+            return
+        col = self.embeddings_column
+
+        def rows():                      # streamed block by block: the bank is never held twice on the host
+            for blk in blocks():
+                for row in blk:
+                    yield {col: row}
+
+        if n:
+            feats = datasets.Features({col: datasets.Sequence(datasets.Value("float32"))})
+            ds = datasets.Dataset.from_generator(rows, features=feats)
+        else:
+            ds = datasets.Dataset.from_dict({col: np.zeros((0, d), np.float32)})
+        ds.save_to_disk(str(self.embeddings_folder) + sfx)
 
     def load(self) -> None:
         """Load `mips/index.faiss` (+ `max_norm.pkl`) written by `save()` OR by the reference

@@ -16,6 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from . import index as _index
 from ._lib import METRIC_IP as METRIC_INNER_PRODUCT, OUT_IP, OUT_L2
 
 
@@ -100,6 +101,51 @@ def gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     return out.view(world, nq, k, rec)
 
 
+def alltoall_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """The exchange step of the data-parallel TRAINING search through torch.distributed (the C-ABI NCCL path
+    does the same with one ncclSend/ncclRecv group): `packed` uint8 [G * B, k, 16] holds this shard's lists
+    for every rank's B queries, rank major; rank r receives [G, B, k, 16] = every shard's lists of ITS queries."""
+    world = dist.get_world_size(group)
+    gb, k, rec = packed.shape
+    if gb % world:
+        raise ValueError("first dimension must be world * B")
+    out = torch.empty_like(packed)
+    dist.all_to_all_single(out, packed.contiguous(), group=group)
+    return out.view(world, gb // world, k, rec)
+
+
+class NcclComm:
+    """An NCCL communicator owned by libmips_b200 (include/mips_b200.h, "cross-GPU step through NCCL"): rank 0
+    draws the unique id through the C ABI, the existing torch.distributed group (any backend) carries its 128
+    bytes to the other ranks, and every rank calls ncclCommInitRank through the C ABI. Afterwards the search
+    step never touches torch.distributed: the collective is enqueued by the C side on the caller's stream."""
+
+    def __init__(self, device: torch.device, group=None):
+        self.L = _lib.lib()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.ptr = C.c_void_p()
+        if self.L.mips_nccl_version() < 0:
+            raise _lib.MipsError("NCCL is not available to libmips_b200 (libnccl.so.2 not loadable)")
+        box = [None]
+        if self.rank == 0:
+            buf = C.create_string_buffer(128)
+            _lib.check(self.L.mips_nccl_unique_id(buf))
+            box[0] = bytes(buf.raw)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=group)
+        with torch.cuda.device(device):
+            _lib.check(self.L.mips_nccl_comm_init(C.byref(self.ptr), self.world, self.rank,
+                                                  C.create_string_buffer(box[0], 128), device.index))
+
+    def close(self) -> None:
+        if self.ptr is not None and self.ptr.value:
+            torch.cuda.synchronize(self.device)
+            self.L.mips_nccl_comm_destroy(self.ptr)
+            self.ptr = None
+
+
 class PeerExchange:
     """Exchange buffers of the peer-memory variant of the cross-GPU step (include/mips_b200.h, "peer-memory
     exchange"): every rank cudaMallocs one buffer, the ranks swap CUDA IPC handles once and map each
@@ -107,7 +153,7 @@ class PeerExchange:
     rank's records into every rank's buffer over NVLink and the final merge kernel waits on arrival flags.
     Two slot sets alternate between consecutive searches. Creation and close() are collective."""
 
-    FLAG_BYTES = 128          # one slot's flags: up to 32 ranks x uint32
+    FLAG_BYTES = 256          # one slot's flags: 32 arrival flags (uint32) + the time-out flag (word 32)
 
     def __init__(self, device: torch.device, group, nq_cap: int, k_cap: int):
         self.L = _lib.lib()
@@ -157,6 +203,17 @@ class PeerExchange:
         return (self.seq, bufs, flags, self.own + slot * self.slot_bytes,
                 self.own + self.flags_off + slot * self.FLAG_BYTES)
 
+    def timed_out(self) -> int:
+        """Sequence number of the last search whose wait for a peer expired (0 = none). Synchronises."""
+        worst = 0
+        for slot in (0, 1):
+            v = C.c_uint32(0)
+            _lib.check(self.L.mips_xchg_timeout_seq(self.device.index,
+                                                    C.c_void_p(self.own + self.flags_off + slot * self.FLAG_BYTES),
+                                                    C.byref(v)))
+            worst = max(worst, int(v.value))
+        return worst
+
     def close(self) -> None:
         if self.own is None:
             return
@@ -171,8 +228,19 @@ class PeerExchange:
 
 
 class ShardedFlatIndex:
-    """B200FlatIndex per rank + NCCL all-gather + K2 merge. Queries are replicated on all ranks
-    (every rank passes the same xq) and every rank ends with the full result."""
+    """B200FlatIndex per rank + one collective + K2 merge.
+
+    `search`: queries are replicated on all ranks (every rank passes the same xq) and every rank ends with
+    the full result. `search_dp`: the data-parallel TRAINING step — each rank passes its OWN batch, as every
+    DDP rank of the reference calls `self.mips(queries=...)` with its own queries
+    (sotasum/retriever_generator.py:143-153, driven per rank by lightning_model.py:188-216), and gets the
+    global top-k of its own queries.
+
+    exchange = "native" (default on NCCL groups): the whole step is ONE C-ABI call; the collective is a raw
+    ncclAllGather (or ncclSend/ncclRecv group) enqueued by libmips_b200 on the caller's stream over its own
+    communicator — no torch.distributed dispatch in the step, capturable in a CUDA graph (`capture`).
+    "torch": torch.distributed collectives between the C-ABI calls (any backend; the first round's path).
+    "p2p": peer-memory exchange fused into the merge kernels (CUDA IPC over NVLink)."""
 
     def __init__(self, local_index, group=None, exchange: Optional[str] = None):
         self.local = local_index
@@ -180,12 +248,14 @@ class ShardedFlatIndex:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.counts = [0] * self.world
-        # "nccl": one all-gather of the packed lists; "p2p": peer-memory exchange fused into the merge
-        # kernels (CUDA IPC over NVLink, no collective launch per search); MIPS_B200_EXCHANGE overrides
-        self.exchange = exchange or os.environ.get("MIPS_B200_EXCHANGE", "nccl")
-        if self.exchange not in ("nccl", "p2p"):
-            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {self.exchange!r}")
+        default = "native" if dist.get_backend(group) == "nccl" else "torch"
+        self.exchange = exchange or os.environ.get("MIPS_B200_EXCHANGE", default)
+        if self.exchange == "nccl":           # round-1 name of the torch.distributed path
+            self.exchange = "torch"
+        if self.exchange not in ("native", "torch", "p2p"):
+            raise ValueError(f"exchange must be 'native', 'torch' or 'p2p', got {self.exchange!r}")
         self._xchg: Optional[PeerExchange] = None
+        self._comm: Optional[NcclComm] = None
 
     @property
     def d(self) -> int:
@@ -198,6 +268,19 @@ class ShardedFlatIndex:
     @property
     def ntotal(self) -> int:
         return int(sum(self.counts))
+
+    def adopt(self, other: "ShardedFlatIndex") -> None:
+        """Take over the communicator / exchange buffers of `other` (the index this one replaces after a
+        memory refresh) instead of creating new ones; `other` must not be used afterwards."""
+        self.exchange = other.exchange
+        self._comm, other._comm = other._comm, None
+        self._xchg, other._xchg = other._xchg, None
+
+    def comm(self) -> NcclComm:
+        """The library-owned NCCL communicator (created collectively on first use)."""
+        if self._comm is None:
+            self._comm = NcclComm(self.local.device, self.group)
+        return self._comm
 
     def add_local(self, x, normalize: bool = False) -> None:
         """Append this rank's rows, then agree on the id space: global id = offset[rank] + row.
@@ -212,28 +295,106 @@ class ShardedFlatIndex:
         self.local.phi = phi
         return phi
 
+    # ------------------------------------------------------------------ outputs
+    def _alloc_outputs(self, nq: int, k: int, want, L):
+        return _index.alloc_outputs(self.local.device, nq, k, want, L)
+
+    def _prep(self, xq, ignore_ids):
+        loc = self.local
+        if not isinstance(xq, torch.Tensor):
+            xq = torch.as_tensor(xq)
+        if xq.dim() != 2:
+            raise ValueError("Shape of query must be 2D")
+        if xq.shape[1] != loc.d:
+            raise ValueError(f"Query vectors must have dimension {loc.d}, got {xq.shape[1]}")
+        xq = xq.detach().to(device=loc.device, dtype=torch.float32).contiguous()
+        ign = None
+        if ignore_ids is not None:
+            ign = torch.as_tensor(ignore_ids).to(device=loc.device, dtype=torch.int64).contiguous()
+            if ign.shape != (xq.shape[0],):
+                raise ValueError("ignore_ids must have one id per query")
+        return xq, ign
+
+    def _native_call(self, dp: bool, xq, ign, k, out, L, normalize_queries, out_mode, beta, beta_bias, algo):
+        """ONE C-ABI call for the whole sharded step (mips_search_sharded / mips_search_sharded_dp)."""
+        comm = self.comm().ptr if self.world > 1 else None
+        return _index.sharded_step(self.local, comm, self.world, self.rank, dp, xq, ign, k, out, L,
+                                   normalize_queries, out_mode, beta, beta_bias, algo)
+
+    # ------------------------------------------------------------------ replicated queries
     def search(self, xq, k: int, ignore_ids=None, want: Iterable[str] = ("scores", "ids"),
                L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
                beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> dict:
+        k = self.local._check_k(k)
         if self.exchange == "p2p" and self.world > 1 and self.local.dtype == "bf16":
             r = self._search_p2p(xq, k, ignore_ids, set(want), L, normalize_queries, out_mode, beta, beta_bias, algo)
             if r is not None:
                 return r
+        if self.exchange in ("native", "p2p"):
+            xq, ign = self._prep(xq, ignore_ids)
+            out = self._alloc_outputs(xq.shape[0], k, want, L)
+            return self._native_call(False, xq, ign, k, out, L, normalize_queries, out_mode, beta, beta_bias, algo)
         packed, qn2 = self.local.search_local_packed(xq, k, ignore_ids=ignore_ids,
                                                      normalize_queries=normalize_queries, algo=algo)
         gathered = gather_packed(packed, self.group) if self.world > 1 else packed.unsqueeze(0)
         return self.local.merge_packed(gathered, qn2, k, want=want, out_mode=out_mode, mem_len=L,
                                        beta=beta, beta_bias=beta_bias)
 
+    # ------------------------------------------------------------------ data-parallel training step
+    def search_dp(self, xq_local, k: int, ignore_ids=None, want: Iterable[str] = ("scores", "ids"),
+                  L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
+                  beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> dict:
+        """Each rank passes its OWN [B, d] queries (same B on every rank; ignore_ids given on all ranks or on
+        none) and receives the global top-k of its own queries: all-gather queries -> one local search of
+        G*B queries -> all-to-all of 16-byte records -> per-rank merge with the fused doc outputs
+        (SURVEY §8e "DP-training variant"). Collective."""
+        k = self.local._check_k(k)
+        xq, ign = self._prep(xq_local, ignore_ids)
+        B = xq.shape[0]
+        if self.exchange in ("native", "p2p") or self.world == 1:
+            out = self._alloc_outputs(B, k, want, L)
+            return self._native_call(True, xq, ign, k, out, L, normalize_queries, out_mode, beta, beta_bias, algo)
+        q_all = torch.empty((self.world * B, xq.shape[1]), dtype=torch.float32, device=xq.device)
+        dist.all_gather_into_tensor(q_all, xq, group=self.group)
+        ign_all = None
+        if ign is not None:
+            ign_all = torch.empty((self.world * B,), dtype=torch.int64, device=xq.device)
+            dist.all_gather_into_tensor(ign_all, ign, group=self.group)
+        packed, qn2 = self.local.search_local_packed(q_all, k, ignore_ids=ign_all,
+                                                     normalize_queries=normalize_queries, algo=algo)
+        mine = alltoall_packed(packed, self.group)
+        return self.local.merge_packed(mine, qn2[self.rank * B:(self.rank + 1) * B].contiguous(), k, want=want,
+                                       out_mode=out_mode, mem_len=L, beta=beta, beta_bias=beta_bias)
+
+    # ------------------------------------------------------------------ CUDA graph of the whole step
+    def capture(self, nq: int, k: int, dp: bool = False, with_ignore: bool = False,
+                want: Iterable[str] = ("scores", "ids"), L: Optional[int] = None, normalize_queries: bool = False,
+                out_mode: Optional[int] = None, beta: float = 1.0, beta_bias: float = 0.0,
+                algo: str = "auto") -> "GraphedSearch":
+        """Capture query prep -> K1 -> local merge -> NCCL collective -> final merge as ONE CUDA graph over
+        static buffers (collective: every rank captures). Replays cost one launch; results land in
+        `.out` (static tensors, overwritten by the next replay)."""
+        if self.exchange not in ("native", "p2p") and self.world > 1:
+            raise ValueError("capture needs the native exchange (the C-ABI NCCL step)")
+        k = self.local._check_k(k)
+        return _index.GraphedSearch(
+            self.local, int(nq), k, with_ignore, want, L,
+            lambda xq, ign, out: self._native_call(dp, xq, ign, k, out, L, normalize_queries, out_mode, beta,
+                                                   beta_bias, algo))
+
     # ------------------------------------------------------------------ peer-memory exchange
+    def check_exchange(self) -> None:
+        """Raise if a peer-memory search timed out waiting for a peer (its queries came back with ids -1);
+        the index switches to the NCCL exchange for the following searches."""
+        if self._xchg is not None and self._xchg.timed_out():
+            self.exchange = "native" if dist.get_backend(self.group) == "nccl" else "torch"
+            raise _lib.MipsError("peer-memory exchange: a peer's list did not arrive in time; "
+                                 "falling back to the NCCL exchange")
+
     def _search_p2p(self, xq, k, ignore_ids, want, L, normalize_queries, out_mode, beta, beta_bias, algo):
         loc = self.local
         lib = _lib.lib()
-        if not isinstance(xq, torch.Tensor):
-            xq = torch.as_tensor(xq)
-        if xq.dim() != 2 or xq.shape[1] != loc.d:
-            raise ValueError(f"Query vectors must be [nq, {loc.d}]")
-        xq = xq.detach().to(device=loc.device, dtype=torch.float32).contiguous()
+        xq, ign = self._prep(xq, ignore_ids)
         nq, k = xq.shape[0], int(k)
         if nq == 0 or nq > 148 * 128:
             return None                                   # chunked searches keep the NCCL path
@@ -244,16 +405,7 @@ class ShardedFlatIndex:
         seq, bufs, flags, my_buf, my_flags = self._xchg.next_search(nq, k)
         dev = loc.device
         qn2 = torch.empty((nq,), dtype=torch.float32, device=dev)
-        ign = None if ignore_ids is None else torch.as_tensor(ignore_ids).to(device=dev, dtype=torch.int64).contiguous()
-        D = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        I = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        cosine = torch.empty((nq, k), dtype=torch.float32, device=dev) if want & {"cosine", "memory_bias", "doc_prob"} else None
-        doc_prob = torch.empty((nq, k), dtype=torch.float32, device=dev) if "doc_prob" in want else None
-        mbias = None
-        if "memory_bias" in want:
-            if not L or L < 1:
-                raise ValueError("memory_bias needs L (memory_seq_len) >= 1")
-            mbias = torch.empty((nq, k * int(L)), dtype=torch.float32, device=dev)
+        out = self._alloc_outputs(nq, k, want, L)
         if out_mode is None:
             out_mode = OUT_IP if loc.metric_type == METRIC_INNER_PRODUCT else OUT_L2
         vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
@@ -262,20 +414,17 @@ class ShardedFlatIndex:
             _lib.check(lib.mips_search_local_xchg(loc._h, vp(xq), nq, k, int(normalize_queries), vp(ign), loc.id_offset,
                                                   loc._algo_code(algo), vp(bufs), vp(flags), self.world, seq, vp(qn2), st))
             _lib.check(lib.mips_merge_xchg(C.c_void_p(my_buf), C.c_void_p(my_flags), self.world, seq, nq, k, k,
-                                           loc.metric_type, int(out_mode), float(loc.phi), vp(qn2), None, vp(D), vp(I),
-                                           vp(cosine), vp(doc_prob), float(beta), float(beta_bias), vp(mbias),
-                                           int(L or 0), st))
-        out = {"scores": D, "ids": I}
-        if cosine is not None:
-            out["cosine"] = cosine
-        if doc_prob is not None:
-            out["doc_prob"] = doc_prob
-        if mbias is not None:
-            out["memory_bias"] = mbias
+                                           loc.metric_type, int(out_mode), float(loc.phi), vp(qn2), None,
+                                           vp(out["scores"]), vp(out["ids"]), vp(out.get("cosine")),
+                                           vp(out.get("doc_prob")), float(beta), float(beta_bias),
+                                           vp(out.get("memory_bias")), int(L or 0), st))
         return out
 
     def close(self) -> None:
-        """Collective: release the peer-memory exchange buffers (no-op for the NCCL exchange)."""
+        """Collective: release the peer-memory exchange buffers and the library-owned communicator."""
         if self._xchg is not None:
             self._xchg.close()
             self._xchg = None
+        if self._comm is not None:
+            self._comm.close()
+            self._comm = None

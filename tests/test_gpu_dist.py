@@ -51,11 +51,53 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         assert np.array_equal(ids, I2)
         np.testing.assert_allclose(r["cosine"].cpu().numpy(), o.doc_scores(xq, xb[ids]), rtol=1e-4, atol=1e-5)
         assert r["memory_bias"].shape == (nq, k * 4)
+        # the three spellings of the replicated-query step agree bit for bit: ONE C-ABI call with a raw
+        # ncclAllGather on the step's stream ("native", the default), torch.distributed between C-ABI calls
+        # ("torch"), and a CUDA-graph replay of the native step
+        xq_t = torch.from_numpy(xq).cuda()
+        assert mp._sharded.exchange == "native"
+        sh_t = m.ShardedFlatIndex(mp.index, dist.group.WORLD, exchange="torch")
+        sh_t.counts = mp._sharded.counts
+        want = ("scores", "ids", "cosine", "doc_prob", "memory_bias")
+        a = mp._sharded.search(xq_t, k, want=want, L=3, ignore_ids=torch.as_tensor(ign), out_mode=2)
+        b = sh_t.search(xq_t, k, want=want, L=3, ignore_ids=torch.as_tensor(ign), out_mode=2)
+        g = mp._sharded.capture(nq, k, with_ignore=True, want=want, L=3, out_mode=2)
+        c = g.replay(xq_t, torch.as_tensor(ign).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(a["ids"].cpu().numpy(), I_ref)
+        for key in ("ids", "scores", "cosine", "doc_prob", "memory_bias"):
+            assert torch.equal(a[key], b[key]) and torch.equal(a[key], c[key]), key
+        c2 = g.replay(xq_t.flip(0), torch.as_tensor(ign).cuda().flip(0))      # a replay with new inputs
+        torch.cuda.synchronize()
+        assert np.array_equal(c2["ids"].cpu().numpy(), I_ref[::-1])
+        # data-parallel TRAINING step: every rank its OWN queries (retriever_generator.py:143-153 under DDP);
+        # native (ncclSend/ncclRecv group) and torch (all_to_all_single) spellings agree with the oracle
+        B = nq // world
+        mine = slice(rank * B, (rank + 1) * B)
+        for shx in (mp._sharded, sh_t):
+            r = shx.search_dp(xq_t[mine], k, ignore_ids=torch.as_tensor(ign[mine]), want=("scores", "ids", "cosine"))
+            torch.cuda.synchronize()
+            assert np.array_equal(r["ids"].cpu().numpy(), I_ref[mine]), shx.exchange
+            np.testing.assert_allclose(r["cosine"].cpu().numpy(),
+                                       o.doc_scores(xq[mine], xb[r["ids"].cpu().numpy()]), rtol=1e-4, atol=1e-5)
+        r = mp._sharded.search_dp(xq_t[mine], k)               # without ignored ids (no second all-gather)
+        assert np.array_equal(r["ids"].cpu().numpy(), I2[mine])
+        gd = mp._sharded.capture(B, k, dp=True)
+        r = gd.replay(xq_t[mine])
+        torch.cuda.synchronize()
+        assert np.array_equal(r["ids"].cpu().numpy(), I2[mine])
+        # a memory refresh keeps the communicator (no new NCCL communicator / exchange buffers per rebuild)
+        comm_before = mp._sharded._comm
+        mp.begin_refresh(len(rows))
+        mp.refresh_add(torch.from_numpy(xb[rows.start:rows.stop]).cuda())
+        mp.commit_refresh(100)
+        assert mp._sharded._comm is comm_before and comm_before is not None
+        D3, I3 = mp.search(mp._prepare_query(xq), ign, k)
+        assert np.array_equal(np.asarray(I3), I_ref)
         # peer-memory exchange (CUDA IPC over NVLink, fused into the merge kernels): same answers as the
         # NCCL all-gather, search after search (the two slot sets alternate), with and without extras
         sh = m.ShardedFlatIndex(mp.index, dist.group.WORLD, exchange="p2p")
         sh.counts = mp._sharded.counts
-        xq_t = torch.from_numpy(xq).cuda()
         for it in range(5):
             kk = k if it % 2 == 0 else 3
             a = sh.search(xq_t, kk, want=("scores", "ids", "cosine"), out_mode=0)
@@ -65,7 +107,9 @@ def _worker(rank, world, port, n, d, nq, k, ret):
             assert torch.equal(a["cosine"], b["cosine"])
         a = sh.search(xq_t[:7], k, ignore_ids=torch.as_tensor(ign[:7]))
         assert np.array_equal(a["ids"].cpu().numpy(), I_ref[:7])
+        sh.check_exchange()                                    # no peer wait timed out
         sh.close()
+        mp._sharded.close()
         ret[rank] = True
     finally:
         dist.destroy_process_group()

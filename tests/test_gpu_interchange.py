@@ -230,6 +230,27 @@ def test_double_buffered_refresh_serves_old_bank_until_commit(cuda_device):
     assert np.array_equal(np.asarray(i2), np.asarray(i_old))
 
 
+def test_refresh_add_waits_for_the_producer_of_the_block(cuda_device):
+    """The refreshed rows come out of encoder kernels on the CALLER's stream; the ingest on the side stream must
+    not read a block before its producer has written it. A long-running kernel queue on the main stream
+    precedes the write of the block: without the stream dependency the back shard would ingest zeros."""
+    n, d = 4096, 256
+    mips = pkg.Mips(pkg.MipsConfig(mips_metric_type=0, mips_normalize=False, bank_dtype="fp32"))
+    mips.build_index(np.ones((8, d), dtype=np.float32))
+    mips.begin_refresh(n, d)
+    blk = torch.zeros((n, d), device=cuda_device)
+    big = torch.randn((8192, 8192), device=cuda_device)
+    for _ in range(20):                                   # ~100 ms of queued work ahead of the block's producer
+        big = big @ big
+        big = big / big.abs().max()
+    src = torch.randn((n, d), device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(1))
+    blk.copy_(src)                                        # the "encoder" writes the block after that queue
+    mips.refresh_add(blk)
+    mips.commit_refresh(100)
+    torch.cuda.synchronize()
+    assert np.array_equal(mips.index.reconstruct_n(), src.cpu().numpy())
+
+
 # ----------------------------------------------------------------------------------------- N3 (forward)
 def test_copy_mixture_matches_reference_statements(cuda_device, golden):
     """Golden from retriever_generator.py:391-404 executed on seeded tensors, then a BART-sized vocabulary

@@ -90,6 +90,46 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         dist.destroy_process_group()
 
 
+def _dp_worker(rank, world, port, n, d, B, k, ret):
+    """Exchange logic of the data-parallel search (every rank its own B queries): all-gather of the queries,
+    local search of all G*B (the oracle stands in for the CUDA-only K1), all-to-all of the 16-byte records,
+    merge of the rank's own B queries == unsharded search of those queries."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(17)
+        xb = rng.standard_normal((n, d), dtype=np.float32)
+        xq_all = rng.standard_normal((world * B, d), dtype=np.float32)
+        mine = xq_all[rank * B:(rank + 1) * B]
+        rows = sharded.shard_range(n, rank, world)
+        q_all = torch.empty((world * B, d), dtype=torch.float32)
+        dist.all_gather_into_tensor(q_all, torch.from_numpy(mine.copy()))
+        assert np.array_equal(q_all.numpy(), xq_all)
+        D, I = o.flat_search(xb[rows.start:rows.stop], q_all.numpy(), k)
+        rec = np.zeros((world * B, k), dtype=np.dtype([("key", "<f4"), ("xn2", "<f4"), ("id", "<i8")]))
+        rec["key"], rec["id"] = D, np.where(I >= 0, I + rows.start, -1)
+        packed = torch.from_numpy(rec.view(np.uint8).reshape(world * B, k, 16).copy())
+        got = sharded.alltoall_packed(packed)
+        assert got.shape == (world, B, k, 16)
+        back = got.numpy().reshape(world, B, k * 16).view(rec.dtype).reshape(world, B, k)
+        cat_s = back["key"].transpose(1, 0, 2).reshape(B, -1)
+        cat_i = back["id"].transpose(1, 0, 2).reshape(B, -1)
+        order = np.lexsort((cat_i, -cat_s), axis=1)[:, :k]
+        D_ref, I_ref = o.flat_search(xb, mine, k)
+        assert np.array_equal(np.take_along_axis(cat_i, order, 1), I_ref)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_exchange_gloo():
+    world, port = 2, _free_port()
+    with mp.Manager() as man:
+        ret = man.dict()
+        mp.spawn(_dp_worker, args=(world, port, 3001, 24, 5, 4, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
+
+
 def test_two_rank_exchange_gloo():
     world, port = 2, _free_port()
     with mp.Manager() as man:

@@ -152,3 +152,19 @@ def test_copy_mixture_matches_reference_statements(golden):
     out = o.copy_mixture(g["logits"], g["gen_gate"], g["copy_probs"], g["copy_seq"])
     np.testing.assert_allclose(out, g["outs"], rtol=2e-6, atol=2e-6)
     assert np.all(np.isfinite(out))
+
+
+def test_chunked_cpu_search_equals_flat_search():
+    """The torch sgemm + top-k + merge leg that bench.py times as the CPU baseline returns what the
+    restated flat search returns (ids identical, (score desc, id asc) across chunk boundaries)."""
+    rng = np.random.default_rng(3)
+    xb = rng.standard_normal((4099, 48), dtype=np.float32)
+    xb[1000] = xb[3000]                      # an exact tie across two chunks
+    xq = rng.standard_normal((21, 48), dtype=np.float32)
+    xq[0] = xb[1000]
+    D1, I1 = o.flat_search(xb, xq, 8)
+    D2, I2 = o.flat_search_chunked(xb, xq, 8, chunk_rows=1500)
+    assert np.array_equal(I1, I2)
+    np.testing.assert_allclose(D1, D2, rtol=1e-6, atol=1e-5)
+    D3, I3 = o.flat_search_chunked(xb[:5], xq, 8)
+    assert (I3[:, 5:] == -1).all() and np.isinf(D3[:, 5:]).all()
