@@ -285,17 +285,47 @@ int mips_search_sharded_dp(mips_handle h, void* nccl_comm, int n_ranks, int rank
                            int out_mode, float* D, int64_t* I, float* cosine, float* doc_prob, float beta,
                            float beta_bias, float* memory_bias, int mem_len, void* stream);
 
-/* ---- generation / copy mixture (next row N3, forward) --------------------------------------- */
+/* ---- generation / copy mixture (next row N3) ------------------------------------------------- */
 
 /* Replaces reference sotasum/retriever_generator.py:391-404:
  *   out[r, :] = log(gen_gate[r] * softmax(logits[r, :]) + scatter_add(copy_probs[r, :] at copy_seq[b, :]) + eps)
  * with r = b * rows_per_batch + t, logits / out fp32 [n_rows, V], gen_gate [n_rows], copy_probs [n_rows, S]
  * (already gated: copy_gate * attention, decoder_own.py:538), copy_seq int64 [n_rows / rows_per_batch, S]
  * (tokens outside [0, V) are skipped), eps = 1e-7 in the reference. One pass over the logits, the
- * vocabulary row lives in shared memory: V <= 56000. Forward only (generation / evaluation); all
- * pointers device memory; async on `stream`. */
+ * vocabulary row lives in shared memory: V <= 56000. All pointers device memory; async on `stream`.
+ *   mips_copy_mixture      forward (generation / evaluation)
+ *   mips_copy_mixture_fwd  forward that also saves the row statistics (stats [n_rows, 2]: max and
+ *                          sum of exp(logits - max)) for the backward; stats may be NULL
+ *   mips_copy_mixture_bwd  training: for the upstream gradient dout [n_rows, V] writes dlogits [n_rows, V],
+ *                          dgate [n_rows] and dcopy [n_rows, S] (the gradient of copy_probs) in one pass over
+ *                          (logits, out, dout) */
 int mips_copy_mixture(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
                       int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, void* stream);
+int mips_copy_mixture_fwd(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
+                          int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, float* stats,
+                          void* stream);
+int mips_copy_mixture_bwd(const float* logits, const float* out, const float* dout, const float* gen_gate,
+                          const float* stats, const int64_t* copy_seq, int64_t n_rows, int rows_per_batch, int V, int S,
+                          float* dlogits, float* dgate, float* dcopy, void* stream);
+
+/* ---- score-biased copy attention (next row N3) ------------------------------------------------ */
+
+/* The elementwise / row-wise part of the copy decoder's ONE-head cross attention, reference
+ * sotasum/decoder_own.py:110-134 (the GEMMs at :108 and :164 stay library GEMMs of the host):
+ *   probs[r, s] = softmax_s( scores[r, s] + (beta * doc_scores[b, s / mem_len] + beta_bias) + mask[b, s] )
+ * r = b * T + t; scores / probs fp32 [B*T, S]; doc_scores [B, n_docs] = `mips_scores` — its broadcast
+ * `memory_bias` (retriever_generator.py:188-192) is never materialised (mem_len = 1, n_docs = S gives a general
+ * per-token attention_bias); mask additive [B, S] (0 / finfo.min) or NULL; beta_dev = device {beta, beta_bias}
+ * (trainable parameters; read on the device, no host sync) or NULL to use the two scalars. S <= 16384.
+ *   _fwd: one pass (read scores, write probs; probs may alias scores)
+ *   _bwd: dscores = probs * (dprobs - sum_s probs * dprobs) and, fused, the reduction that carries the gradient
+ *         to the retriever: doc_grad[b, j] += sum_t sum_{s in doc j} dscores (zeroed by the caller; NULL to skip).
+ *         d doc_scores = beta * doc_grad, d beta = sum(doc_grad * doc_scores), d beta_bias = sum(doc_grad). */
+int mips_copy_attention_softmax_fwd(const float* scores, const float* doc_scores, int n_docs, int mem_len, float beta,
+                                    float beta_bias, const float* beta_dev, const float* mask, int B, int T, int S,
+                                    float* probs, void* stream);
+int mips_copy_attention_softmax_bwd(const float* probs, const float* dprobs, int n_docs, int mem_len, int B, int T, int S,
+                                    float* dscores, float* doc_grad, void* stream);
 
 #ifdef __cplusplus
 }

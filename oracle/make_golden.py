@@ -10,7 +10,9 @@ reference sources by AST / source segment and executed unmodified:
                              faiss.normalize_L2 replaced by its documented contract)
   sotasum/pretrain.py        retriever_metrics
   sotasum/retriever_generator.py   the doc-score statements :158-172 and :188-192, the copy/generation
-                             mixture statements :391-404
+                             mixture statements :391-404 (+ their autograd gradients)
+  sotasum/decoder_own.py     the score-biased copy attention statements :102-134 and :160-176 of
+                             LEDDecoderAttention.forward (+ their autograd gradients)
 
 Run here (needs /root/reference):   python oracle/make_golden.py
 The .npz files are small and committed; the GPU box never reads /root/reference.
@@ -201,6 +203,55 @@ def main() -> None:
     exec(compile(code, str(rg), "exec"), ns)
     np.savez_compressed(OUT / "copy_mixture.npz", logits=logits.numpy(), gen_gate=gen_gate.numpy(),
                         copy_probs=copy_probs.numpy(), copy_seq=copy_seq.numpy(), outs=ns["outs"].numpy())
+    # gradients of the mixture through the reference's own statements (autograd over the in-place scatter_add_)
+    lg = logits.clone().requires_grad_(True)
+    gg = gen_gate.clone().requires_grad_(True)
+    cpg = copy_probs.clone().requires_grad_(True)
+    ns = {"torch": torch, "F": F, "gen_gate": gg, "copy_probs": cpg,
+          "decoder_outputs": types.SimpleNamespace(logits=lg),
+          "decoder_hidden_states": torch.zeros(B, T, 8), "encoder_copy_sequence": copy_seq}
+    exec(compile(code, str(rg), "exec"), ns)
+    w_out = torch.tensor(rng7.standard_normal((B, T, V), dtype=np.float32))
+    (ns["outs"] * w_out).sum().backward()
+    np.savez_compressed(OUT / "copy_mixture_grad.npz", w_out=w_out.numpy(), d_logits=lg.grad.numpy(),
+                        d_gen_gate=gg.grad.numpy(), d_copy_probs=cpg.grad.numpy())
+
+    # ---- G8: the score-biased copy attention (decoder_own.py:102-134 + :160-176), ONE head like the copy decoder
+    # (its alignment is `.squeeze(1)`-ed at decoder_own.py:525), forward and autograd gradients; attention_bias is
+    # the memory_bias broadcast of retriever_generator.py:188-192 built from per-document scores
+    dec = REF / "decoder_own.py"
+    code = _statements(dec, 102, 134) + "\n" + _statements(dec, 160, 176)
+    rng8 = np.random.default_rng(8080)
+    B, T, K, L, D = 3, 5, 4, 6, 16
+    S = K * L
+    me = types.SimpleNamespace(num_heads=1, head_dim=D, dropout=0.0, training=False,
+                               beta=torch.tensor([1.3], requires_grad=True),
+                               beta_bias=torch.tensor([-0.2], requires_grad=True))
+    me._shape = lambda tensor, seq_len, bsz: tensor.view(bsz, seq_len, 1, D).transpose(1, 2).contiguous()
+    q_in = torch.tensor(rng8.standard_normal((B, T, D), dtype=np.float32) * 0.5, requires_grad=True)
+    k_in = torch.tensor(rng8.standard_normal((B, 1, S, D), dtype=np.float32), requires_grad=True)
+    v_in = torch.tensor(rng8.standard_normal((B, 1, S, D), dtype=np.float32), requires_grad=True)
+    doc = torch.tensor(rng8.uniform(-1, 1, (B, K)).astype(np.float32), requires_grad=True)      # mips_scores
+    keep = torch.tensor(rng8.uniform(size=(B, S)) < 0.8)
+    keep[:, 0] = True
+    add_mask = torch.zeros(B, S).masked_fill(~keep, torch.finfo(torch.float32).min)
+    attention_mask = add_mask[:, None, None, :].expand(B, 1, T, S)                                # _expand_mask layout
+    attention_bias = doc.unsqueeze(-1).expand(-1, -1, L).reshape(B, -1)                           # rg.py:188-192
+    ns = {"torch": torch, "nn": torch.nn, "self": me, "query_states": q_in, "key_states": k_in, "value_states": v_in,
+          "attention_bias": attention_bias, "attention_mask": attention_mask, "bsz": B, "tgt_len": T, "embed_dim": D}
+    exec(compile(code, str(dec), "exec"), ns)
+    probs, attn_out = ns["attn_weights"], ns["attn_output"]
+    assert probs.shape == (B, T, S) and attn_out.shape == (B, T, D)
+    w_p = torch.tensor(rng8.standard_normal((B, T, S), dtype=np.float32))
+    w_o = torch.tensor(rng8.standard_normal((B, T, D), dtype=np.float32))
+    ((probs * w_p).sum() + (attn_out * w_o).sum()).backward()
+    np.savez_compressed(
+        OUT / "copy_attention.npz", query_states=q_in.detach().numpy(), key_states=k_in.detach().numpy()[:, 0],
+        value_states=v_in.detach().numpy()[:, 0], doc_scores=doc.detach().numpy(), mem_len=np.int64(L),
+        beta=me.beta.detach().numpy(), beta_bias=me.beta_bias.detach().numpy(), add_mask=add_mask.numpy(),
+        attn_weights=probs.detach().numpy(), attn_output=attn_out.detach().numpy(), w_p=w_p.numpy(), w_o=w_o.numpy(),
+        d_query=q_in.grad.numpy(), d_key=k_in.grad.numpy()[:, 0], d_value=v_in.grad.numpy()[:, 0],
+        d_doc_scores=doc.grad.numpy(), d_beta=me.beta.grad.numpy(), d_beta_bias=me.beta_bias.grad.numpy())
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*.npz")):
         print(f"  {f.name}: {f.stat().st_size/1024:.1f} KiB")

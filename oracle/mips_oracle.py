@@ -10,7 +10,9 @@ CODE run in the build container: oracle/make_golden.py AST-extracts `inner_produ
 `get_phi`, `augment_xb`, `augment_xq` (sotasum/mips.py:55-70, 552-560), the body of
 `Mips.search` (mips.py:382-400), `retriever_metrics` (pretrain.py:69-85) and the doc-score
 statements of `SotasumEncoder.forward` (retriever_generator.py:158-172, 188-192) and the
-generation / copy mixture statements (retriever_generator.py:391-404), executes
+generation / copy mixture statements (retriever_generator.py:391-404, with autograd gradients) and the
+score-biased copy attention statements of LEDDecoderAttention.forward (decoder_own.py:102-134, 160-176,
+with autograd gradients), executes
 them on seeded inputs and commits the results under tests/golden/. tests/test_oracle.py checks
 every function below against those fixtures. The faiss-cpu 1.7.4 kernels behind
 `faiss_index.search` are a third-party wheel that is not vendored in /root/reference and not
@@ -234,6 +236,65 @@ def copy_mixture(logits: np.ndarray, gen_gate: np.ndarray, copy_probs: np.ndarra
         for t in range(T):
             np.add.at(probs[b, t], copy_seq[b], copy_probs[b, t].astype(np.float32))
     return np.log(probs + np.float32(eps)).astype(np.float32)
+
+
+def copy_mixture_grad(logits, gen_gate, copy_probs, copy_seq, d_out, eps: float = 1e-7):
+    """Gradients of `copy_mixture` (retriever_generator.py:391-404) for an upstream d_out [B, T, V], float64:
+    with m = gen_gate * p + scatter(copy) + eps, dM = d_out / m: d_gate = sum dM p; d_logits = gate p (dM - sum dM p);
+    d_copy[s] = dM[copy_seq[s]]. Returns (d_logits, d_gen_gate [B, T, 1], d_copy_probs)."""
+    x = logits.astype(np.float64)
+    x = x - x.max(-1, keepdims=True)
+    p = np.exp(x)
+    p /= p.sum(-1, keepdims=True)
+    g = gen_gate.astype(np.float64).reshape(*logits.shape[:2], 1)
+    m = g * p
+    B, T, _ = m.shape
+    for b in range(B):
+        for t in range(T):
+            np.add.at(m[b, t], copy_seq[b], copy_probs[b, t].astype(np.float64))
+    dM = d_out.astype(np.float64) / (m + eps)
+    dot = (dM * p).sum(-1, keepdims=True)
+    d_copy = np.stack([dM[b][:, copy_seq[b]] for b in range(B)])
+    return g * p * (dM - dot), dot, d_copy
+
+
+def copy_attention(query_states, key_states, value_states, doc_scores, mem_len: int, beta: float = 1.0,
+                   beta_bias: float = 0.0, add_mask=None):
+    """The copy decoder's one-head cross attention, decoder_own.py:102-134 and :160-176: logits = q k^T (:108) +
+    beta * attention_bias + beta_bias (:110-114, attention_bias[b, j * mem_len + t] = doc_scores[b, j] =
+    memory_bias of retriever_generator.py:188-192) + additive mask (:123-132); ONE softmax over all memory tokens
+    (:134); output = probs v (:164). q [B, T, D], k / v [B, S, D], doc_scores [B, K], add_mask [B, S].
+    Returns (attn_output [B, T, D], attn_weights [B, T, S]) in float64."""
+    q, k, v = (a.astype(np.float64) for a in (query_states, key_states, value_states))
+    S = k.shape[1]
+    z = q @ k.transpose(0, 2, 1)
+    if doc_scores is not None:
+        bias = np.repeat(doc_scores.astype(np.float64), mem_len, axis=1)[:, :S]
+        z = z + (beta * bias + beta_bias)[:, None, :]
+    if add_mask is not None:
+        z = z + add_mask.astype(np.float64)[:, None, :]
+    z = z - z.max(-1, keepdims=True)
+    p = np.exp(z)
+    p /= p.sum(-1, keepdims=True)
+    return p @ v, p
+
+
+def copy_attention_grad(query_states, key_states, value_states, doc_scores, mem_len: int, beta: float, beta_bias: float,
+                        add_mask, d_out, d_probs):
+    """Gradients of `copy_attention` for upstream d_out [B, T, D] (on attn_output) and d_probs [B, T, S] (on the
+    alignment, which feeds copy_probs at decoder_own.py:538), float64. Returns a dict with d_query, d_key, d_value,
+    d_doc_scores [B, K] (the retriever's signal: beta * sum over the document's tokens and all target positions of
+    dS), d_beta, d_beta_bias."""
+    q, k, v = (a.astype(np.float64) for a in (query_states, key_states, value_states))
+    out, p = copy_attention(q, k, v, doc_scores, mem_len, beta, beta_bias, add_mask)
+    dP = d_probs.astype(np.float64) + d_out.astype(np.float64) @ v.transpose(0, 2, 1)
+    dS = p * (dP - (dP * p).sum(-1, keepdims=True))
+    B, T, S = p.shape
+    K = doc_scores.shape[1]
+    pad = K * mem_len - S
+    G = np.pad(dS.sum(1), ((0, 0), (0, pad))).reshape(B, K, mem_len).sum(-1)
+    return {"d_query": dS @ k, "d_key": dS.transpose(0, 2, 1) @ q, "d_value": p.transpose(0, 2, 1) @ d_out.astype(np.float64),
+            "d_doc_scores": beta * G, "d_beta": (G * doc_scores.astype(np.float64)).sum(), "d_beta_bias": G.sum()}
 
 
 def retriever_metrics(pred: np.ndarray, counts: np.ndarray) -> dict:

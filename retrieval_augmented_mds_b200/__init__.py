@@ -1,10 +1,11 @@
 """retrieval_augmented_mds_b200 — B200-native exact MIPS for the non-parametric memory of
 florianbaud/retrieval-augmented-mds (the `Mips.search` hot path of sotasum/mips.py feeding
 sotasum/retriever_generator.py). CUDA (sm_100a) behind a C ABI; no CPU compute path."""
-from .index import (METRIC_INNER_PRODUCT, METRIC_L2, B200FlatIndex, MemoryTokenStore, IndexFlat, IndexFlatIP, IndexFlatL2,
-                    copy_mixture, index_factory, merge_candidates, normalize_L2, retriever_metrics)
+from .index import (METRIC_INNER_PRODUCT, METRIC_L2, B200FlatIndex, GraphedSearch, MemoryTokenStore, IndexFlat, IndexFlatIP,
+                    IndexFlatL2, index_factory, merge_candidates, normalize_L2, retriever_metrics)
+from .generator_ops import biased_softmax, copy_attention, copy_mixture
 from .faiss_io import read_index, write_index
-from .mips import Mips, MipsConfig
+from .mips import Mips, MipsConfig, MipsModelOutput, RGEncoderModelOutput
 from .sharded import ShardedFlatIndex, balanced_range, shard_range, weighted_ranges
 
 
@@ -27,6 +28,6 @@ def install_faiss_shim() -> str:
     return compat
 
 
-__all__ = ["copy_mixture", "MemoryTokenStore", "retriever_metrics", "read_index", "write_index", "install_faiss_shim", "B200FlatIndex", "IndexFlat", "IndexFlatIP", "IndexFlatL2", "index_factory", "normalize_L2",
+__all__ = ["copy_mixture", "copy_attention", "biased_softmax", "GraphedSearch", "MipsModelOutput", "RGEncoderModelOutput", "MemoryTokenStore", "retriever_metrics", "read_index", "write_index", "install_faiss_shim", "B200FlatIndex", "IndexFlat", "IndexFlatIP", "IndexFlatL2", "index_factory", "normalize_L2",
            "merge_candidates", "METRIC_INNER_PRODUCT", "METRIC_L2", "Mips", "MipsConfig",
            "ShardedFlatIndex", "shard_range", "balanced_range", "weighted_ranges"]

@@ -88,6 +88,10 @@ def lib() -> C.CDLL:
         "mips_gather_rows": (i32, [vp, vp, i64, i64, vp, vp]),
         "mips_gather_tokens": (i32, [vp, vp, i64, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
         "mips_copy_mixture": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, f32, vp, vp]),
+        "mips_copy_mixture_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, f32, vp, vp, vp]),
+        "mips_copy_mixture_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp]),
+        "mips_copy_attention_softmax_fwd": (i32, [vp, vp, i32, i32, f32, f32, vp, vp, i32, i32, i32, vp, vp]),
+        "mips_copy_attention_softmax_bwd": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "mips_retriever_metrics": (i32, [vp, i32, i32, vp, i64, vp, vp, vp, vp, vp, vp]),
         "mips_set_profiling": (i32, [vp, i32]),
         "mips_k1_ms_total": (f32, [vp]),

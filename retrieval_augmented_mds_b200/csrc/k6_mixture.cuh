@@ -51,7 +51,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 2) copy_mix
     const float* __restrict__ gen_gate,     // [R]
     const float* __restrict__ copy_probs,   // [R, S]
     const int64_t* __restrict__ copy_seq,   // [R / rows_per_batch, S]
-    int rows_per_batch, int V, int S, float eps, float* __restrict__ out) {
+    int rows_per_batch, int V, int S, float eps, float* __restrict__ out,
+    float* __restrict__ stats) {            // [R, 2] row max and sum of exp(logits - max) for the backward, or null
   extern __shared__ float row[];            // this CTA's half of the vocabulary row
   __shared__ float red[THREADS / 32];
   __shared__ float peer_val[2];             // written by the peer CTA: its half's max, then its half's sum
@@ -89,6 +90,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 2) copy_mix
   sum = block_reduce(sum, red, false);
   if (threadIdx.x == 0) st_peer_f32(&peer_val[1], peer, sum);
   ptx::cluster_sync_all();
+  if (stats && rank == 0 && threadIdx.x == 0) {
+    stats[2 * r] = mx;
+    stats[2 * r + 1] = sum + peer_val[1];
+  }
   const float scale = gen_gate[r] / (sum + peer_val[1]);
   for (int v = threadIdx.x; v < n; v += THREADS) row[v] *= scale;
   __syncthreads();

@@ -23,6 +23,7 @@
 #include "k4_metrics.cuh"
 #include "k5_gather.cuh"
 #include "k6_mixture.cuh"
+#include "k7_attention.cuh"
 #include "mips_b200.h"
 #include "nccl_dl.h"
 
@@ -1290,17 +1291,9 @@ int mips_search_sharded_dp(mips_handle h, void* nccl_comm, int n_ranks, int rank
 #undef NCCL_TRY
 
 // ------------------------------------------------------------------------------------------ mixture
-int mips_copy_mixture(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
-                      int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, void* stream) {
-  if (n_rows < 0 || rows_per_batch < 1 || V < 1 || S < 0) return set_err(MIPS_E_INVALID, "bad shape");
-  if (n_rows == 0) return 0;
-  if (n_rows % rows_per_batch != 0) return set_err(MIPS_E_INVALID, "n_rows must be a multiple of rows_per_batch");
-  if (!logits || !gen_gate || !out || (S > 0 && (!copy_probs || !copy_seq))) return set_err(MIPS_E_INVALID, "null buffers");
-  if (V > mix::MAX_V)
-    return set_err(MIPS_E_UNSUPPORTED, "vocabulary of %d does not fit one CTA's shared memory (max %d)", V, mix::MAX_V);
-  if (n_rows > 0x7fffffff) return set_err(MIPS_E_INVALID, "too many rows");
-  // the opt-in is per DEVICE (and this entry point has no handle): run on the device that owns `logits`
-  // and set the attribute there on every call (a few hundred ns on the host, no device work)
+static int mixture_device(const float* logits) {
+  // the shared-memory opt-in is per DEVICE (and these entry points have no handle): run on the device that owns
+  // `logits` and set the attributes there on every call (a few hundred ns on the host, no device work)
   cudaPointerAttributes pa;
   CUDA_TRY(cudaPointerGetAttributes(&pa, logits));
   if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged)
@@ -1308,11 +1301,92 @@ int mips_copy_mixture(const float* logits, const float* gen_gate, const float* c
   CUDA_TRY(cudaSetDevice(pa.device));
   CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 mix::MAX_HALF * static_cast<int>(sizeof(float))));
+  CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                mix::MAX_HALF * static_cast<int>(sizeof(float))));
+  return 0;
+}
+
+int mips_copy_mixture_fwd(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
+                          int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, float* stats,
+                          void* stream) {
+  if (n_rows < 0 || rows_per_batch < 1 || V < 1 || S < 0) return set_err(MIPS_E_INVALID, "bad shape");
+  if (n_rows == 0) return 0;
+  if (n_rows % rows_per_batch != 0) return set_err(MIPS_E_INVALID, "n_rows must be a multiple of rows_per_batch");
+  if (!logits || !gen_gate || !out || (S > 0 && (!copy_probs || !copy_seq))) return set_err(MIPS_E_INVALID, "null buffers");
+  if (V > mix::MAX_V)
+    return set_err(MIPS_E_UNSUPPORTED, "vocabulary of %d does not fit one CTA's shared memory (max %d)", V, mix::MAX_V);
   if (n_rows > 0x3fffffff) return set_err(MIPS_E_INVALID, "too many rows");
+  int rc = mixture_device(logits);
+  if (rc) return rc;
   mix::copy_mixture_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS, static_cast<size_t>((V + 1) / 2) * sizeof(float),
                              static_cast<cudaStream_t>(stream)>>>(logits, gen_gate, copy_probs, copy_seq,
-                                                                  rows_per_batch, V, S, eps, out);
+                                                                  rows_per_batch, V, S, eps, out, stats);
   LAUNCH_CHECK("copy_mixture_kernel");
+  return 0;
+}
+
+int mips_copy_mixture(const float* logits, const float* gen_gate, const float* copy_probs, const int64_t* copy_seq,
+                      int64_t n_rows, int rows_per_batch, int V, int S, float eps, float* out, void* stream) {
+  return mips_copy_mixture_fwd(logits, gen_gate, copy_probs, copy_seq, n_rows, rows_per_batch, V, S, eps, out, nullptr,
+                               stream);
+}
+
+int mips_copy_mixture_bwd(const float* logits, const float* out, const float* dout, const float* gen_gate,
+                          const float* stats, const int64_t* copy_seq, int64_t n_rows, int rows_per_batch, int V, int S,
+                          float* dlogits, float* dgate, float* dcopy, void* stream) {
+  if (n_rows < 0 || rows_per_batch < 1 || V < 1 || S < 0) return set_err(MIPS_E_INVALID, "bad shape");
+  if (n_rows == 0) return 0;
+  if (n_rows % rows_per_batch != 0) return set_err(MIPS_E_INVALID, "n_rows must be a multiple of rows_per_batch");
+  if (!logits || !out || !dout || !gen_gate || !stats || !dlogits || !dgate || (S > 0 && (!copy_seq || !dcopy)))
+    return set_err(MIPS_E_INVALID, "null buffers");
+  if (V > mix::MAX_V)
+    return set_err(MIPS_E_UNSUPPORTED, "vocabulary of %d does not fit one CTA's shared memory (max %d)", V, mix::MAX_V);
+  if (n_rows > 0x3fffffff) return set_err(MIPS_E_INVALID, "too many rows");
+  int rc = mixture_device(logits);
+  if (rc) return rc;
+  mix::copy_mixture_bwd_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS,
+                                 static_cast<size_t>((V + 1) / 2) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      logits, out, dout, gen_gate, stats, copy_seq, rows_per_batch, V, S, dlogits, dgate, dcopy);
+  LAUNCH_CHECK("copy_mixture_bwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ copy attention
+int mips_copy_attention_softmax_fwd(const float* scores, const float* doc_scores, int n_docs, int mem_len, float beta,
+                                    float beta_bias, const float* beta_dev, const float* mask, int B, int T, int S,
+                                    float* probs, void* stream) {
+  if (B < 0 || T < 0 || S < 1) return set_err(MIPS_E_INVALID, "bad shape");
+  if (B == 0 || T == 0) return 0;
+  if (!scores || !probs) return set_err(MIPS_E_INVALID, "null buffers");
+  if (doc_scores && (n_docs < 1 || mem_len < 1 || static_cast<int64_t>(n_docs) * mem_len < S))
+    return set_err(MIPS_E_INVALID, "doc_scores needs n_docs * mem_len >= S");
+  if (S > cattn::MAX_S) return set_err(MIPS_E_UNSUPPORTED, "S = %d memory tokens exceed one CTA's shared memory (max %d)", S, cattn::MAX_S);
+  const size_t smem = static_cast<size_t>(S) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(cattn::biased_softmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                cattn::MAX_S * static_cast<int>(sizeof(float))));
+  cattn::biased_softmax_fwd_kernel<<<static_cast<unsigned>(static_cast<int64_t>(B) * T), cattn::THREADS, smem,
+                                     static_cast<cudaStream_t>(stream)>>>(scores, doc_scores, n_docs, mem_len, beta, beta_bias,
+                                                                          beta_dev, mask, T, S, probs);
+  LAUNCH_CHECK("biased_softmax_fwd_kernel");
+  return 0;
+}
+
+int mips_copy_attention_softmax_bwd(const float* probs, const float* dprobs, int n_docs, int mem_len, int B, int T, int S,
+                                    float* dscores, float* doc_grad, void* stream) {
+  if (B < 0 || T < 0 || S < 1) return set_err(MIPS_E_INVALID, "bad shape");
+  if (B == 0 || T == 0) return 0;
+  if (!probs || !dprobs || !dscores) return set_err(MIPS_E_INVALID, "null buffers");
+  if (doc_grad && (n_docs < 1 || mem_len < 1 || static_cast<int64_t>(n_docs) * mem_len < S))
+    return set_err(MIPS_E_INVALID, "doc_grad needs n_docs * mem_len >= S");
+  if (doc_grad && n_docs > cattn::MAX_S)
+    return set_err(MIPS_E_UNSUPPORTED, "%d documents exceed the per-row shared-memory bins (max %d)", n_docs, cattn::MAX_S);
+  const size_t smem = doc_grad ? static_cast<size_t>(n_docs) * sizeof(float) : 0;
+  CUDA_TRY(cudaFuncSetAttribute(cattn::biased_softmax_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                cattn::MAX_S * static_cast<int>(sizeof(float))));
+  cattn::biased_softmax_bwd_kernel<<<static_cast<unsigned>(static_cast<int64_t>(B) * T), cattn::THREADS, smem,
+                                     static_cast<cudaStream_t>(stream)>>>(probs, dprobs, n_docs, mem_len, T, S, dscores,
+                                                                          doc_grad);
+  LAUNCH_CHECK("biased_softmax_bwd_kernel");
   return 0;
 }
 

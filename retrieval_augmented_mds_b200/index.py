@@ -573,29 +573,3 @@ class MemoryTokenStore:
                                                 self.pad_id, self.bos_id, self.eos_id, *[_ptr(o) for o in outs], st))
         return {"memory_input_ids": outs[0], "attention_mask": outs[1], "memory_attention_mask": outs[2],
                 "global_attention_mask": outs[3]}
-
-
-def copy_mixture(logits: torch.Tensor, gen_gate: torch.Tensor, copy_probs: torch.Tensor, copy_seq: torch.Tensor,
-                 eps: float = 1e-7) -> torch.Tensor:
-    """log(gen_gate * softmax(logits) + scatter_add(copy_probs at copy_seq) + eps) in one pass over the logits
-    (retriever_generator.py:391-404, forward): logits [B, T, V], gen_gate [B, T, 1], copy_probs [B, T, S],
-    copy_seq int64 [B, S] -> [B, T, V] fp32, all CUDA."""
-    if not (logits.is_cuda and gen_gate.is_cuda and copy_probs.is_cuda and copy_seq.is_cuda):
-        raise ValueError("copy_mixture runs on the GPU: pass CUDA tensors (no CPU compute path)")
-    if logits.dim() != 3 or copy_probs.dim() != 3 or copy_seq.dim() != 2:
-        raise ValueError("expected logits [B, T, V], copy_probs [B, T, S], copy_seq [B, S]")
-    B, T, V = logits.shape
-    S = copy_probs.shape[2]
-    if copy_probs.shape[:2] != (B, T) or copy_seq.shape != (B, S) or gen_gate.numel() != B * T:
-        raise ValueError("inconsistent shapes")
-    dev = logits.device
-    logits = logits.to(torch.float32).contiguous()
-    gen_gate = gen_gate.to(torch.float32).contiguous()
-    copy_probs = copy_probs.to(torch.float32).contiguous()
-    copy_seq = copy_seq.to(torch.int64).contiguous()
-    out = torch.empty((B, T, V), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        check(_lib.lib().mips_copy_mixture(_ptr(logits), _ptr(gen_gate), _ptr(copy_probs), _ptr(copy_seq), B * T, T, V, S,
-                                           float(eps), _ptr(out), st))
-    return out

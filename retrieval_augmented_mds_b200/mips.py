@@ -390,18 +390,23 @@ class Mips:
         except ImportError:
             return
         col = self.embeddings_column
-
-        def rows():                      # streamed block by block: the bank is never held twice on the host
-            for blk in blocks():
-                for row in blk:
-                    yield {col: row}
-
         if n:
+            # streamed block by block through an Arrow file (memory-mapped back): the bank is never held twice
+            from datasets.arrow_writer import ArrowWriter
             feats = datasets.Features({col: datasets.Sequence(datasets.Value("float32"))})
-            ds = datasets.Dataset.from_generator(rows, features=feats)
+            tmp_arrow = str(self.mips_folder / f".embeddings_stream{sfx}.arrow")
+            writer = ArrowWriter(features=feats, path=tmp_arrow)
+            for blk in blocks():
+                writer.write_batch({col: blk})
+            writer.finalize()
+            ds = datasets.Dataset.from_file(tmp_arrow)
         else:
+            tmp_arrow = None
             ds = datasets.Dataset.from_dict({col: np.zeros((0, d), np.float32)})
         ds.save_to_disk(str(self.embeddings_folder) + sfx)
+        if tmp_arrow is not None:
+            del ds
+            Path(tmp_arrow).unlink(missing_ok=True)
 
     def load(self) -> None:
         """Load `mips/index.faiss` (+ `max_norm.pkl`) written by `save()` OR by the reference

@@ -251,7 +251,7 @@ def test_refresh_add_waits_for_the_producer_of_the_block(cuda_device):
     assert np.array_equal(mips.index.reconstruct_n(), src.cpu().numpy())
 
 
-# ----------------------------------------------------------------------------------------- N3 (forward)
+# ----------------------------------------------------------------------------------------- N3 (forward; gradients: test_gpu_generator_ops.py)
 def test_copy_mixture_matches_reference_statements(cuda_device, golden):
     """Golden from retriever_generator.py:391-404 executed on seeded tensors, then a BART-sized vocabulary
     against the oracle and against the reference's own sequence of torch ops on the GPU."""
