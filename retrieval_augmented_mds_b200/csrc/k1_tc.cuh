@@ -252,6 +252,8 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
     const bool live = qrow < p.nq;
     const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
     float thr = -CUDART_INF_F;
+    PoolState pool;   // pooling across splits is used by the CTA-pair kernel only
+    pool.init(0);
 
     int it = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++it) {
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // accumulator is in registers: MMA may reuse it
-      fold_tile<kL2, NGRP>(v, p.xnorm2, tile * ACC_N, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst);
+      fold_tile<kL2, NGRP, false>(v, p.xnorm2, tile * ACC_N, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst, pool);
     }
 
     if (live) {

@@ -74,9 +74,12 @@ struct Params {
   unsigned long long cache_hint;
   int* pace;        // [n_splits, n_qpairs] tiles issued so far by each pair (zeroed before the launch), or null
   int pace_window;  // a pair never runs more than this many tiles ahead of the slowest pair of its split
+  uint32_t* pool;   // [n_qpairs * 256, n_splits] ordered image of every split's m-th best admitted key per query
+                    // (zeroed before the launch = not published); kPool kernels only: pooled admission threshold, k1_topk.cuh
+  int pool_m;       // m = ceil(k / n_splits) in [1, 4]
 };
 
-template <bool kL2, int SKCH>
+template <bool kL2, int SKCH, bool kPool>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_tc2_kernel(
     const __grid_constant__ CUtensorMap tmap_bank, const __grid_constant__ CUtensorMap tmap_q,
     const Params p) {
@@ -314,10 +317,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
     float thr = -CUDART_INF_F;
     const bool live = qrow < p.nq;
     const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
+    PoolState pool;
+    pool.init(kPool ? p.pool_m : 0);
+    uint32_t* pub = kPool ? p.pool + static_cast<size_t>(qrow) * p.n_splits : nullptr;
+    float published = -CUDART_INF_F;
 
     int it = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++it) {
       const int acc = it & 1;
+      if (kPool && live && (it < 8 || (it & 7) == 0)) {
+        // T = min over the splits of their published m-th best (0 = not yet published: no pooling yet); the
+        // loads are in flight while this warp waits for the accumulator below
+        uint32_t t = 0xffffffffu;
+        for (int sp = 0; sp < p.n_splits; ++sp) {
+          uint32_t u;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(u) : "l"(pub + sp) : "memory");
+          t = min(t, u);
+        }
+        if (t > 0u) {
+          pool.floor = fmaxf(pool.floor, ordered_to_f32(t - 1u));
+          thr = fmaxf(thr, pool.floor);
+        }
+      }
       ptx::mbar_wait(tfull_bar(acc), acc_par(it));
       __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent insert path
       ptx::tc_fence_after();
@@ -333,7 +354,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(tempty0_leader + 8u * acc);   // accumulator is in registers
-      fold_tile<kL2, 4>(v, p.xnorm2, id0, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst);
+      fold_tile<kL2, 4, kPool>(v, p.xnorm2, id0, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst, pool);
+      if (kPool && live) {
+        const float mth = pool.mth();
+        if (mth > published) {   // published values only grow
+          published = mth;
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(pub + split), "r"(f32_to_ordered(mth)) : "memory");
+        }
+      }
     }
 
     if (live) {

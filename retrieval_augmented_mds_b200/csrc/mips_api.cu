@@ -93,6 +93,7 @@ struct mips_index_s {
   int* part_ids = nullptr;     size_t part_ids_bytes = 0;
   int* ign_local = nullptr;    size_t ign_bytes = 0;
   int* pace = nullptr;         size_t pace_bytes = 0;
+  uint32_t* pool = nullptr;    size_t pool_bytes = 0;       // pooled admission thresholds [nq_pad, n_splits]
   __nv_bfloat16* q_hi = nullptr; size_t q_hi_bytes = 0;     // bf16-rounded prepared queries
   float* q_res2 = nullptr;     size_t q_res2_bytes = 0;     // |q - bf16(q)|^2
   float* cand_key = nullptr;   size_t cand_key_bytes = 0;   // approximate keys of the kc candidates
@@ -276,7 +277,9 @@ static int set_kernel_attrs(mips_index_s* h) {
 #undef TC_ATTR
   CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 4 * 8));
 #define TC2_ATTR(L2, K)                                                                        \
-  CUDA_TRY(cudaFuncSetAttribute(tc2::search_tc2_kernel<L2, K>,                                 \
+  CUDA_TRY(cudaFuncSetAttribute(tc2::search_tc2_kernel<L2, K, false>,                          \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_LIMIT)); \
+  CUDA_TRY(cudaFuncSetAttribute(tc2::search_tc2_kernel<L2, K, true>,                           \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_LIMIT))
   TC2_ATTR(false, 4); TC2_ATTR(true, 4); TC2_ATTR(false, 6); TC2_ATTR(true, 6);
   TC2_ATTR(false, 2); TC2_ATTR(true, 2);
@@ -338,7 +341,7 @@ int mips_destroy(mips_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* dev[] = {h->bank, h->norm2, h->max_norm2_bits, h->q_prep, h->q_norm2, h->part_key,
-                 h->part_ids, h->ign_local, h->pace, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->sh_local, h->sh_gath, h->sh_qn2, h->dp_q, h->dp_ign, h->hq, h->hign, h->hkey, h->hids,
+                 h->part_ids, h->ign_local, h->pace, h->pool, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->sh_local, h->sh_gath, h->sh_qn2, h->dp_q, h->dp_ign, h->hq, h->hign, h->hkey, h->hids,
                  h->hxn2, h->hqn2, h->hD, h->hI};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -584,7 +587,8 @@ int mips_reconstruct(mips_handle h, int64_t row0, int64_t n, float* out, int out
 // K1, CTA-pair tensor-core kernel over a bf16 row matrix described by `tmap_bank` (the bf16 bank, or
 // the bf16 shadow of an fp32 bank). Leaves [n_splits, nq, k] candidate lists in h->part_key / part_ids.
 static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_bfloat16* q_bf16, int nq,
-                      int nq_pad, int k, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out) {
+                      int nq_pad, int k, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out,
+                      bool allow_pool = true) {
     int rc = encode_query_tmap(h, q_bf16, nq_pad);
     if (rc) return rc;
     const int n_tiles = static_cast<int>((h->ntotal + tc2::TILE_N - 1) / tc2::TILE_N);
@@ -611,7 +615,8 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     p.n_splits = n_splits;
     // 48 KiB stages when three of them fit (k <= 8 at d = 768), else 32 KiB: A/B on one board with pacing on,
     // 12.16 ms vs 12.33 ms per launch on the 10M x 768 bank
-    int skch = (h->d_pad / tc2::KCH) % 6 == 0 && tc2::pick_stages(h->d_pad, k, 6) >= 3 ? 6 : 4;
+    // (one query pair = HBM bound: 32 KiB stages, one more of them in flight: 10M x 768, nq=256: 3.05 vs 3.12 ms)
+    int skch = (h->d_pad / tc2::KCH) % 6 == 0 && tc2::pick_stages(h->d_pad, k, 6) >= 3 && n_qpairs > 1 ? 6 : 4;
     static const int skch_env = env_int("MIPS_TC2_SKCH", 0);   // tuning experiments only
     if (skch_env == 2 || skch_env == 4 || skch_env == 6) skch = skch_env;
     while (skch > 2 && tc2::pick_stages(h->d_pad, k, skch) < 2) skch -= 2;
@@ -631,12 +636,32 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
       CUDA_TRY(cudaMemsetAsync(h->pace, 0, pb, st));
       p.pace = h->pace;
     }
+    // pooled admission threshold across the splits of a query (k1_topk.cuh). Measured on one board (pool on / off):
+    // 250k rows x 1024 queries, k=32: 0.42 / 0.45 ms; 10M rows, k=64: 12.3 / 12.6 ms; but k=8: 12.65 / 12.15 ms
+    // (10M x 1024), 4.2 / 3.4 ms (10M x 256, 74 splits to poll): the polling loads and the extra registers cost
+    // more than the few admissions a small k has to save — a separate kernel instance, used for k >= 32 only
+    p.pool = nullptr;
+    p.pool_m = (k + n_splits - 1) / n_splits;
+    static const int pool_env = env_int("MIPS_TC2_POOL", -1);   // tuning: 0 never, 1 whenever it is valid
+    const bool pool_wanted = pool_env < 0 ? k >= 32 : pool_env != 0;
+    if (allow_pool && pool_wanted && n_splits >= 2 && p.pool_m <= 4) {
+      const size_t pb = static_cast<size_t>(nq_pad) * n_splits * sizeof(uint32_t);
+      rc = grow(&h->pool, &h->pool_bytes, pb);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemsetAsync(h->pool, 0, pb, st));
+      p.pool = h->pool;
+    }
     const size_t smem = tc2::smem_bytes(h->d_pad, k, p.stages, skch);
     const unsigned grid = static_cast<unsigned>(2 * n_qpairs * n_splits);
-#define TC2_LAUNCH(K)                                                                            \
-  do {                                                                                           \
-    if (l2) tc2::search_tc2_kernel<true, K><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p);  \
-    else    tc2::search_tc2_kernel<false, K><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p); \
+#define TC2_LAUNCH(K)                                                                                         \
+  do {                                                                                                        \
+    if (p.pool) {                                                                                             \
+      if (l2) tc2::search_tc2_kernel<true, K, true><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p);   \
+      else    tc2::search_tc2_kernel<false, K, true><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p);  \
+    } else {                                                                                                  \
+      if (l2) tc2::search_tc2_kernel<true, K, false><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p);  \
+      else    tc2::search_tc2_kernel<false, K, false><<<grid, tc2::THREADS, smem, st>>>(tmap_bank, h->tmap_q, p); \
+    }                                                                                                         \
   } while (0)
     if (skch == 6) TC2_LAUNCH(6); else if (skch == 4) TC2_LAUNCH(4); else TC2_LAUNCH(2);
 #undef TC2_LAUNCH
@@ -813,7 +838,8 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     if (nq <= tc::BLOCK_M && h->d_pad <= tc::MAX_DPAD)
       rc = launch_tc(h, h->tmap_shadow64, h->q_hi, nq, round_up_i(nq, tc::BLOCK_M), m, 64, ign_local, l2, st, &n_parts);
     else
-      rc = launch_tc2(h, h->tmap_shadow64, h->q_hi, nq, nq_pad, m, ign_local, l2, st, &n_parts);
+      rc = launch_tc2(h, h->tmap_shadow64, h->q_hi, nq, nq_pad, m, ign_local, l2, st, &n_parts,
+                      /*allow_pool=*/false);   // the certificate reasons about every split's OWN list
     if (rc) return rc;
     rc = launch_merge_local(h, h->part_key, h->part_ids, nullptr, n_parts, nq, m, kc, 0, h->cand_key, h->cand_rows,
                             nullptr, nullptr, nullptr, st, "merge_topk_kernel<candidates>");

@@ -378,7 +378,9 @@ class GraphedSearch:
     def __init__(self, local: "B200FlatIndex", nq: int, k: int, with_ignore: bool, want, L, call):
         dev = local.device
         self.nq, self.k = nq, k
-        self.xq = torch.zeros((nq, local.d), dtype=torch.float32, device=dev)
+        # random placeholder queries: all-zero queries tie every row of the bank, the worst case of the exact
+        # fp32 search (every query fails its certificate and takes the slow fallback during the warm-up)
+        self.xq = torch.randn((nq, local.d), dtype=torch.float32, device=dev)
         self.ignore_ids = torch.full((nq,), -1, dtype=torch.int64, device=dev) if with_ignore else None
         self.out = alloc_outputs(dev, nq, k, want, L)
         side = torch.cuda.Stream(device=dev)
