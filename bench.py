@@ -333,6 +333,9 @@ def run_ours(args) -> None:
     from retrieval_augmented_mds_b200 import _lib
     from retrieval_augmented_mds_b200.sharded import ShardedFlatIndex, balanced_range
 
+    import faulthandler
+    faulthandler.dump_traceback_later(1200, exit=True)   # a stuck collective must end the run, not hold the box
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -340,12 +343,18 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py needs a B200: the search path is CUDA only (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_fd = 1
     if world > 1:
-        # NCCL's communicator lines must stay visible to whoever launched the run, and stdout must stay the one
-        # JSON line: INFO (init lines only) unless the caller chose a level, written to stderr
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's communicator lines must stay visible to whoever launched the run (its NCCL_DEBUG level is
+        # respected; INFO / INIT when none is set) and stdout must stay the ONE JSON line: everything this
+        # process writes to fd 1 (NCCL logs to the C stdout) is routed to stderr, the JSON line goes to the
+        # original stdout
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world and rank == 0:
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
@@ -539,8 +548,8 @@ def run_ours(args) -> None:
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_sample_leg(nq, d, k, n)
-        print(json.dumps(line))
         sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if sh is not None:
         sh.close()
     if world > 1:

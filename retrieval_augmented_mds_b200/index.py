@@ -394,7 +394,16 @@ class GraphedSearch:
         with torch.cuda.graph(self.graph):
             call(self.xq, self.ignore_ids, self.out)
 
+    def close(self) -> None:
+        """Destroy the graph (required before the NCCL communicator it captured can be destroyed)."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.xq.device)
+            self.graph.reset()
+            self.graph = None
+
     def replay(self, xq: Optional[torch.Tensor] = None, ignore_ids: Optional[torch.Tensor] = None) -> dict:
+        if self.graph is None:
+            raise RuntimeError("this captured search was closed (its index was refreshed or closed)")
         if xq is not None:
             self.xq.copy_(xq, non_blocking=True)
         if ignore_ids is not None:

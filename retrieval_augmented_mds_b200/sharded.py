@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from typing import Iterable, Optional
 
 import torch
@@ -256,6 +257,7 @@ class ShardedFlatIndex:
             raise ValueError(f"exchange must be 'native', 'torch' or 'p2p', got {self.exchange!r}")
         self._xchg: Optional[PeerExchange] = None
         self._comm: Optional[NcclComm] = None
+        self._graphs = []            # weak references to the CUDA graphs captured over the communicator
 
     @property
     def d(self) -> int:
@@ -271,10 +273,19 @@ class ShardedFlatIndex:
 
     def adopt(self, other: "ShardedFlatIndex") -> None:
         """Take over the communicator / exchange buffers of `other` (the index this one replaces after a
-        memory refresh) instead of creating new ones; `other` must not be used afterwards."""
+        memory refresh) instead of creating new ones; `other` must not be used afterwards (graphs captured
+        over it point at the old shard and are released)."""
+        other._release_graphs()
         self.exchange = other.exchange
         self._comm, other._comm = other._comm, None
         self._xchg, other._xchg = other._xchg, None
+
+    def _release_graphs(self) -> None:
+        for ref in self._graphs:
+            g = ref()
+            if g is not None:
+                g.close()
+        self._graphs = []
 
     def comm(self) -> NcclComm:
         """The library-owned NCCL communicator (created collectively on first use)."""
@@ -377,10 +388,12 @@ class ShardedFlatIndex:
         if self.exchange not in ("native", "p2p") and self.world > 1:
             raise ValueError("capture needs the native exchange (the C-ABI NCCL step)")
         k = self.local._check_k(k)
-        return _index.GraphedSearch(
+        g = _index.GraphedSearch(
             self.local, int(nq), k, with_ignore, want, L,
             lambda xq, ign, out: self._native_call(dp, xq, ign, k, out, L, normalize_queries, out_mode, beta,
                                                    beta_bias, algo))
+        self._graphs.append(weakref.ref(g))
+        return g
 
     # ------------------------------------------------------------------ peer-memory exchange
     def check_exchange(self) -> None:
@@ -421,7 +434,10 @@ class ShardedFlatIndex:
         return out
 
     def close(self) -> None:
-        """Collective: release the peer-memory exchange buffers and the library-owned communicator."""
+        """Collective: release the captured graphs, the peer-memory exchange buffers and the library-owned
+        communicator. The graphs go FIRST: NCCL keeps a communicator alive (ncclCommDestroy blocks) while a
+        CUDA graph that captured one of its collectives exists."""
+        self._release_graphs()
         if self._xchg is not None:
             self._xchg.close()
             self._xchg = None

@@ -20,10 +20,13 @@ def _free_port():
 
 
 def _worker(rank, world, port, n, d, nq, k, ret):
+    import faulthandler
+
     import torch.distributed as dist
 
     import retrieval_augmented_mds_b200 as m
 
+    faulthandler.dump_traceback_later(240, exit=True)     # a stuck collective must not hold the GPU box
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
