@@ -64,6 +64,8 @@ typedef struct mips_index_s* mips_handle;
 #define MIPS_E_NCCL -5     /* NCCL missing or a collective failed */
 
 #define MIPS_MAX_K 64      /* per-pass top-k capacity of the search kernels */
+#define MIPS_MAX_K_MULTIPASS 2048   /* largest k of the multi-pass entry points (mips_search_host; passes of MIPS_MAX_K
+                                       through mips_search_local_after) */
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 
@@ -125,6 +127,17 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
                       float* out_key, int64_t* out_ids, float* out_xnorm2, float* out_qnorm2,
                       void* stream);
 
+/* One pass of a MULTI-PASS search (k > MIPS_MAX_K; faiss accepts any k, reference mips.py:383-386): like
+ * mips_search_local / mips_search_local_packed, but only rows strictly AFTER (after_key[j], after_id[j]) in the
+ * total order (ranking key descending, global id ascending) are eligible for query j — pass the last result of
+ * the previous pass (its out_key and out_ids; a query that ran out of rows: key -inf, id INT64_MAX). after_key /
+ * after_id device [nq], both NULL = unbounded. Give out_key / out_ids (+ optional out_xnorm2) or out_packed.
+ * fp32 banks run bounded passes on the exact fp32 FMA kernel. 1 <= k <= MIPS_MAX_K per pass. Async on `stream`. */
+int mips_search_local_after(mips_handle h, const float* q, int nq, int k, int q_normalize, const int64_t* ignore_ids,
+                            int64_t id_offset, int algo, const float* after_key, const int64_t* after_id,
+                            float* out_key, int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
+                            void* stream);
+
 /* k-way merge of n_parts candidate lists per query (after the cross-GPU all-gather, or of a
  * single list) + output transform + the doc-score arithmetic of retriever_generator.py:158-193.
  *   cand_key/cand_ids/cand_xnorm2  device [n_parts, nq, k_in]   (cand_xnorm2 may be NULL if
@@ -157,7 +170,8 @@ int mips_merge_packed(const void* cand_packed, int n_parts, int nq, int k_in, in
 
 /* End-to-end host call: what `Mips.search` does today with numpy in / numpy out
  * (reference mips.py:382-400). H2D of queries, K1, K2, D2H of (D, I); sync.
- * xq host fp32 [nq, d]; ignore_ids host int64 [nq] or NULL; D host fp32 [nq,k]; I host int64 [nq,k]. */
+ * xq host fp32 [nq, d]; ignore_ids host int64 [nq] or NULL; D host fp32 [nq,k]; I host int64 [nq,k].
+ * 1 <= k <= MIPS_MAX_K_MULTIPASS: k > MIPS_MAX_K runs ceil(k / MIPS_MAX_K) bounded passes (exact). */
 int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normalize,
                      const int64_t* ignore_ids, int out_mode, float* D, int64_t* I, void* stream);
 

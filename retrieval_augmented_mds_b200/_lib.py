@@ -18,7 +18,8 @@ METRIC_IP, METRIC_L2 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2, ALGO_TCX = 0, 1, 2, 3, 4, 5
 OUT_IP, OUT_L2, OUT_AUGL2 = 0, 1, 2
-MAX_K = 64
+MAX_K = 64                 # per-pass capacity of the search kernels (MIPS_MAX_K)
+MAX_K_MULTIPASS = 2048     # largest k of the multi-pass paths (MIPS_MAX_K_MULTIPASS)
 
 _lib = None
 
@@ -58,6 +59,7 @@ def lib() -> C.CDLL:
         "mips_normalize_l2": (i32, [vp, i64, i32, i32, i32, vp]),
         "mips_reconstruct": (i32, [vp, i64, i64, vp, i32, vp]),
         "mips_search_local": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp]),
+        "mips_search_local_after": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "mips_merge": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp,
                              f32, f32, vp, i32, vp]),
         "mips_search_local_packed": (i32, [vp, vp, i32, i32, i32, vp, i64, i32, vp, vp, vp]),

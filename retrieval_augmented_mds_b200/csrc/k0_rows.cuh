@@ -153,3 +153,25 @@ __global__ void ignore_to_local_kernel(const int64_t* __restrict__ ignore_ids, i
   const int64_t l = ignore_ids[i] - id_offset;
   out[i] = (l >= 0 && l < ntotal) ? static_cast<int>(l) : -1;
 }
+
+// Multi-pass search (k > MIPS_MAX_K): pass p+1 only admits rows strictly AFTER the last result of pass p in the
+// total order (key descending, id ascending). The bound id (global int64) becomes a shard-local row bound: rows
+// with the bound's key are excluded iff row <= bound_row; ids of other shards clamp to -1 / INT_MAX.
+__global__ void bound_to_local_kernel(const int64_t* __restrict__ after_id, int nq, int64_t id_offset,
+                                      int* __restrict__ out_row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int64_t l = after_id[i] - id_offset;
+  out_row[i] = l < 0 ? -1 : (l > 0x7fffffffll ? 0x7fffffff : static_cast<int>(l));
+}
+
+// last column of a [nq, k] result -> the bound of the next pass (a query that ran out of rows, id -1, gets a bound
+// nothing can follow)
+__global__ void take_last_kernel(const float* __restrict__ key, const int64_t* __restrict__ ids, int nq, int k,
+                                 float* __restrict__ after_key, int64_t* __restrict__ after_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int64_t id = ids[static_cast<size_t>(i) * k + (k - 1)];
+  after_key[i] = id < 0 ? -CUDART_INF_F : key[static_cast<size_t>(i) * k + (k - 1)];
+  after_id[i] = id < 0 ? INT64_MAX : id;
+}

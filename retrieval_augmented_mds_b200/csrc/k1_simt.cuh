@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(THREADS, 2) search_simt_kernel(
     const T* __restrict__ q, const T* __restrict__ bank, const float* __restrict__ xnorm2, int nq,
     int64_t ntotal, int d_pad, int k, const int* __restrict__ ignore_local, int n_tiles,
     float* __restrict__ part_key, int* __restrict__ part_ids,
-    const int* __restrict__ tile_active) {   // [n_qtiles] or null: query tiles to (re)compute
+    const int* __restrict__ tile_active,             // [n_qtiles] or null: query tiles to (re)compute
+    const float* __restrict__ after_key = nullptr,   // multi-pass search: only rows strictly after
+    const int* __restrict__ after_row = nullptr) {   // (after_key, after_row) are eligible
   if (tile_active && !tile_active[blockIdx.x]) return;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);          // [2][BK][BM]
@@ -80,6 +82,12 @@ __global__ void __launch_bounds__(THREADS, 2) search_simt_kernel(
       li[i] = -1;
     }
     if (ignore_local && qrow0 + ql < nq) ign = ignore_local[qrow0 + ql];
+  }
+  float bkey = 0.f;
+  int brow = -1;
+  if (after_key && scanner && qrow0 + ql < nq) {
+    bkey = after_key[qrow0 + ql];
+    brow = after_row[qrow0 + ql];
   }
 
   // global->smem loader mapping: 4 consecutive k of one row per thread
@@ -161,7 +169,8 @@ __global__ void __launch_bounds__(THREADS, 2) search_simt_kernel(
         const float s = srow[c];
         if (s > thr) {
           const int64_t id = brow0 + c;
-          if (id < ntotal && id != ign) thr = topk_list_insert(lk, li, k, s, static_cast<int>(id));
+          const bool eligible = !after_key || s < bkey || (s == bkey && id > brow);
+          if (id < ntotal && id != ign && eligible) thr = topk_list_insert(lk, li, k, s, static_cast<int>(id));
         }
       }
     }

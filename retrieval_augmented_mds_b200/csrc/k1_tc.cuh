@@ -68,6 +68,8 @@ struct Params {
   const __nv_bfloat16* q;   // [n_qtiles*128, d_pad] prepared queries (zero padded)
   const float* xnorm2;      // [capacity] (L2 only)
   const int* ignore_local;  // [nq] or null
+  const float* after_key;   // [nq] or null: multi-pass search, only rows strictly after (after_key, after_row) ...
+  const int* after_row;     // ... in the order (key descending, row ascending) are eligible
   float* part_key;          // [n_splits, nq, k]
   int* part_ids;
   int64_t ntotal;
@@ -251,6 +253,8 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
     int worst = 0;
     const bool live = qrow < p.nq;
     const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
+    const float bkey = (p.after_key && live) ? p.after_key[qrow] : 0.f;
+    const int brow = (p.after_key && live) ? p.after_row[qrow] : -1;
     float thr = -CUDART_INF_F;
     PoolState pool;   // pooling across splits is used by the CTA-pair kernel only
     pool.init(0);
@@ -268,7 +272,8 @@ __global__ void __launch_bounds__(THREADS, 1) search_tc_kernel(
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));   // accumulator is in registers: MMA may reuse it
-      fold_tile<kL2, NGRP, false>(v, p.xnorm2, tile * ACC_N, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst, pool);
+      fold_tile<kL2, NGRP, false>(v, p.xnorm2, tile * ACC_N, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst, pool,
+                                      p.after_key != nullptr, bkey, brow);
     }
 
     if (live) {

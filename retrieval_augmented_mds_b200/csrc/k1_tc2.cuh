@@ -67,6 +67,8 @@ struct Params {
   const __nv_bfloat16* q;   // [n_qpairs*256, d_pad] prepared queries (zero padded)
   const float* xnorm2;      // [capacity] (L2 only)
   const int* ignore_local;  // [nq] or null
+  const float* after_key;   // [nq] or null: multi-pass search, only rows strictly after (after_key, after_row) ...
+  const int* after_row;     // ... in the order (key descending, row ascending) are eligible
   float* part_key;          // [n_splits, nq, k]
   int* part_ids;
   int64_t ntotal;
@@ -317,6 +319,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
     float thr = -CUDART_INF_F;
     const bool live = qrow < p.nq;
     const int ign = (p.ignore_local && live) ? p.ignore_local[qrow] : -1;
+    const float bkey = (p.after_key && live) ? p.after_key[qrow] : 0.f;
+    const int brow = (p.after_key && live) ? p.after_row[qrow] : -1;
     PoolState pool;
     pool.init(kPool ? p.pool_m : 0);
     uint32_t* pub = kPool ? p.pool + static_cast<size_t>(qrow) * p.n_splits : nullptr;
@@ -354,7 +358,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) search_t
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(tempty0_leader + 8u * acc);   // accumulator is in registers
-      fold_tile<kL2, 4, kPool>(v, p.xnorm2, id0, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst, pool);
+      fold_tile<kL2, 4, kPool>(v, p.xnorm2, id0, p.ntotal, ign, live, set, p.k, kcap, it == 0, thr, worst, pool,
+                               p.after_key != nullptr, bkey, brow);
       if (kPool && live) {
         const float mth = pool.mth();
         if (mth > published) {   // published values only grow

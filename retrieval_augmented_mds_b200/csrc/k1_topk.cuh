@@ -65,7 +65,8 @@ struct PoolState {
 template <bool kL2, int NG, bool kPool>
 __device__ __forceinline__ void fold_tile(uint32_t (&v)[NG][32], const float* xnorm2, int id0,
                                           int64_t ntotal, int ign, bool live, uint32_t* set, int k, int kcap,
-                                          bool first, float& thr, int& worst, PoolState& pool) {
+                                          bool first, float& thr, int& worst, PoolState& pool,
+                                          bool bounded = false, float bound_key = 0.f, int bound_row = -1) {
   if (kL2) {
     // ranking key for L2: <q,x> - |x|^2/2 (same address for every lane: broadcast loads)
     const float4* xn = reinterpret_cast<const float4*>(xnorm2 + id0);
@@ -81,6 +82,18 @@ __device__ __forceinline__ void fold_tile(uint32_t (&v)[NG][32], const float* xn
       }
     }
   }
+  if (bounded) {
+    // multi-pass search (k > MIPS_MAX_K): only rows strictly after the previous pass's last result in the order
+    // (key descending, row ascending) are eligible; the others leave the tile as -inf (never admitted)
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __uint_as_float(v[g][j]);
+        const bool drop = s > bound_key || (s == bound_key && id0 + g * 32 + j <= bound_row);
+        v[g][j] = drop ? __float_as_uint(-CUDART_INF_F) : v[g][j];
+      }
+  }
   float m = -CUDART_INF_F;
 #pragma unroll
   for (int g = 0; g < NG; ++g)
@@ -92,7 +105,7 @@ __device__ __forceinline__ void fold_tile(uint32_t (&v)[NG][32], const float* xn
     // per column build a candidate bit mask, then a rolled loop visits the few set bits and
     // pulls each score out of its register through a branch-free select tree (pick_col64).
     int filled = 0;
-    if (first && id0 + 64 <= ntotal && (ign < id0 || ign >= id0 + k)) {
+    if (first && !bounded && id0 + 64 <= ntotal && (ign < id0 || ign >= id0 + k)) {
       // first tile of the split: its first k columns ARE the top-k so far. Store them directly (static
       // register indices, no admission calls: 128 admissions of ~300 cycles each otherwise open
       // every launch) and let one call find the worst entry.

@@ -79,13 +79,16 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     const PackedCand* __restrict__ cand_packed,   // !LOCAL: packed input instead of the 3 arrays
     PackedCand* __restrict__ out_packed,          // LOCAL: packed output instead of the 3 arrays
     const int* __restrict__ q_active = nullptr,   // only these queries are merged (others keep their outputs)
-    int stage_cap = 0,                            // LOCAL: shared-memory staging entries per warp (dynamic smem)
+    int stage_cap = 0,                            // shared-memory staging entries per warp (dynamic smem: 8 bytes per
+                                                  // entry LOCAL, 16 bytes FINAL); 0 = read candidates from global memory
     XchgOut xo = XchgOut{nullptr, nullptr, nullptr, 0u, 0},   // LOCAL: publish to the peers
     XchgIn xi = XchgIn{nullptr, 0u, 0, nullptr, 0ull}) {     // FINAL: wait for the peers
   // 2 * MIPS_MAX_K: the candidate merge of the exact fp32 search keeps up to 128 entries per query
   __shared__ float s_key[4][2 * MIPS_MAX_K];
   __shared__ float s_xn2[4][2 * MIPS_MAX_K];
   __shared__ float s_cos[4][2 * MIPS_MAX_K];
+  __shared__ int64_t s_id[4][2 * MIPS_MAX_K];
+  __shared__ int s_pos[4][2 * MIPS_MAX_K];
   __shared__ unsigned int s_hist[4][256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + w;   // 4 queries per block, fewer when the staging area is large
@@ -128,28 +131,40 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
   const int64_t ign = ignore_ids ? ignore_ids[q] : -1;
   const int C = n_parts * k_in;
 
-  // LOCAL with many parts (74 splits x 16..64 entries): every round would re-read all C candidates
-  // from global memory (measured 0.39 ms for 256 queries x 2368 candidates). Stage the query's
-  // candidates in shared memory once; the launch provides stage_cap entries per warp (0 = none).
-  extern __shared__ uint2 s_stage[];
-  uint2* stage = nullptr;
-  if (LOCAL && stage_cap >= C && C > 64) {
-    stage = s_stage + static_cast<size_t>(w) * stage_cap;
+  // Every candidate of the query is read from global memory ONCE, into shared memory (the launch provides
+  // stage_cap entries per warp): LOCAL as {key bits, shard-local row}, FINAL as {key bits, position} + the int64
+  // id. The first version re-read them in every selection round — k_out dependent L2 round trips per query
+  // (ncu launch lists: 28 us for the final merge of 1024 x 32 results, 45 us for a local merge).
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint2* stage = reinterpret_cast<uint2*>(s_dyn) + static_cast<size_t>(w) * stage_cap;
+  int64_t* stage_id = nullptr;          // FINAL only
+  if (!LOCAL) stage_id = reinterpret_cast<int64_t*>(s_dyn + static_cast<size_t>(blockDim.x >> 5) * stage_cap * sizeof(uint2)) +
+                         static_cast<size_t>(w) * stage_cap;
+  const bool staged = stage_cap >= C && C > 0;
+  if (staged) {
     for (int c = lane; c < C; c += 32) {
       const int p = c / k_in, sidx = c - p * k_in;
       const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + sidx;
-      stage[c] = make_uint2(__float_as_uint(cand_key[a]), static_cast<uint32_t>(ids32[a]));
+      if (LOCAL) {
+        stage[c] = make_uint2(__float_as_uint(cand_key[a]), static_cast<uint32_t>(ids32[a]));
+      } else if (cand_packed) {
+        const PackedCand pc = cand_packed[a];
+        stage[c] = make_uint2(__float_as_uint(pc.key), static_cast<uint32_t>(c));
+        stage_id[c] = pc.id;
+      } else {
+        stage[c] = make_uint2(__float_as_uint(cand_key[a]), static_cast<uint32_t>(c));
+        stage_id[c] = ids64[a];
+      }
     }
     __syncwarp();
   }
   int C_eff = C;
-  if (LOCAL && stage) {
+  if (LOCAL && staged && C > 512) {
     // Cut the staged candidates down to the k_out best (plus ties at the cut) BEFORE the ordered
-    // selection rounds, whose cost is k_out x candidates (148 splits x 64 entries x 64 rounds took
-    // 3.7 ms for 128 queries): a 4-pass, 8-bit MSB radix select on the order-preserving integer image
-    // of the keys finds the k_out-th largest key T in O(candidates), then one pass compacts the
-    // entries with key >= T to the front of the staging area. Exact: ties at T all survive and the
-    // rounds below order them by id.
+    // selection rounds (148 splits x 64 entries x 64 rounds took 3.7 ms for 128 queries): a 4-pass, 8-bit MSB
+    // radix select on the order-preserving integer image of the keys finds the k_out-th largest key T in
+    // O(candidates), then one pass compacts the entries with key >= T to the front of the staging area.
+    // Exact: ties at T all survive and the rounds below order them by id.
     unsigned int* hist = s_hist[w];
     uint32_t prefix = 0u, known = 0u;
     int remaining = k_out;
@@ -224,79 +239,107 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     }
   }
 
-  float prev_key = CUDART_INF_F;
-  int64_t prev_id = -1;
-  int n_found = 0;
-  for (int j = 0; j < k_out; ++j) {
-    MergeBest b{-CUDART_INF_F, INT64_MAX, -1};
+  // Selection: k_out rounds; round j picks the best candidate strictly after round j-1's pick in the total order
+  // (key descending, id ascending) — no mutation, duplicates of one (key, id) collapse, shard-count invariant.
+  // Every lane caches the best of ITS candidates that is still eligible; a round is two or three warp REDUX
+  // instructions (max of the ordered keys, min of the ids among the lanes that hold that key) and only the lanes
+  // whose cached candidate was just picked rescan their C / 32 entries.
+  auto scan = [&](uint32_t pk, int64_t pid, uint32_t& bk, int64_t& bid, int& bpos) {
+    bk = 0u;
+    bid = INT64_MAX;
+    bpos = -1;
     for (int c = lane; c < C_eff; c += 32) {
-      int64_t id;
       float key;
-      size_t a = 0;
-      if (LOCAL && stage) {
+      int64_t id;
+      int pos;
+      if (staged) {
         const uint2 e = stage[c];
-        const int32_t l = static_cast<int32_t>(e.y);
-        id = l < 0 ? -1 : id_offset + l;
         key = __uint_as_float(e.x);
+        if (LOCAL) {
+          const int32_t l = static_cast<int32_t>(e.y);
+          id = l < 0 ? -1 : id_offset + l;
+          pos = c;
+        } else {
+          id = stage_id[c];
+          pos = static_cast<int>(e.y);
+        }
       } else {
-        const int p = c / k_in, s = c - p * k_in;
-        a = (static_cast<size_t>(p) * nq + q) * k_in + s;
-      }
-      if (LOCAL && stage) {
-      } else if (LOCAL) {
-        const int32_t l = ids32[a];
-        id = l < 0 ? -1 : id_offset + l;
-        key = cand_key[a];
-      } else if (cand_packed) {
-        const PackedCand pc = cand_packed[a];
-        id = pc.id;
-        key = pc.key;
-      } else {
-        id = ids64[a];
-        key = cand_key[a];
+        const int p = c / k_in, sidx = c - p * k_in;
+        const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + sidx;
+        pos = c;
+        if (LOCAL) {
+          const int32_t l = ids32[a];
+          id = l < 0 ? -1 : id_offset + l;
+          key = cand_key[a];
+        } else if (cand_packed) {
+          const PackedCand pc = cand_packed[a];
+          id = pc.id;
+          key = pc.key;
+        } else {
+          id = ids64[a];
+          key = cand_key[a];
+        }
       }
       if (id < 0 || id == ign) continue;
-      const bool after = (key < prev_key) || (key == prev_key && id > prev_id);
+      const uint32_t ku = f32_to_ordered(key);
+      if (ku == 0u) continue;                                   // (no finite or infinite float maps to 0)
+      const bool after = ku < pk || (ku == pk && id > pid);
       if (!after) continue;
-      if (merge_better(key, id, b.key, b.id)) {
-        b.key = key;
-        b.id = id;
-        b.pos = static_cast<int>(a);
+      if (ku > bk || (ku == bk && id < bid)) {
+        bk = ku;
+        bid = id;
+        bpos = pos;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ok = __shfl_xor_sync(0xffffffffu, b.key, o);
-      const int64_t oi = __shfl_xor_sync(0xffffffffu, b.id, o);
-      const int op = __shfl_xor_sync(0xffffffffu, b.pos, o);
-      if (op >= 0 && (b.pos < 0 || merge_better(ok, oi, b.key, b.id))) {
-        b.key = ok;
-        b.id = oi;
-        b.pos = op;
-      }
-    }
-    if (b.pos < 0) break;
-    prev_key = b.key;
-    prev_id = b.id;
-    n_found = j + 1;
+  };
+  uint32_t bk;
+  int64_t bid;
+  int bpos;
+  scan(0xffffffffu, -1, bk, bid, bpos);
+  int n_found = 0;
+  for (int j = 0; j < k_out; ++j) {
+    const uint32_t wk = __reduce_max_sync(0xffffffffu, bk);
+    if (wk == 0u) break;
+    const bool has = bk == wk;
+    const uint32_t whi = __reduce_min_sync(0xffffffffu, has ? static_cast<uint32_t>(static_cast<uint64_t>(bid) >> 32) : 0xffffffffu);
+    const bool has2 = has && static_cast<uint32_t>(static_cast<uint64_t>(bid) >> 32) == whi;
+    const uint32_t wlo = __reduce_min_sync(0xffffffffu, has2 ? static_cast<uint32_t>(static_cast<uint64_t>(bid)) : 0xffffffffu);
+    const int64_t wid = static_cast<int64_t>((static_cast<uint64_t>(whi) << 32) | wlo);
+    const bool mine = has2 && static_cast<uint32_t>(static_cast<uint64_t>(bid)) == wlo;
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    const int wpos = __shfl_sync(0xffffffffu, bpos, src);
     if (lane == 0) {
-      float xn = 0.f;
-      if (LOCAL) {
-        if (bank_xn2) xn = bank_xn2[b.id - id_offset];
-      } else {
-        if (cand_packed) xn = cand_packed[b.pos].xn2;
-        else if (cand_xn2) xn = cand_xn2[b.pos];
-      }
-      s_key[w][j] = b.key;
-      s_xn2[w][j] = xn;
-      if (LOCAL && xo.n_peers > 0) {
-        const PackedCand rec{b.key, xn, b.id};
-        for (int g = 0; g < xo.n_peers; ++g) xo.bufs[g][static_cast<size_t>(q) * k_out + j] = rec;
-      } else if (LOCAL && out_packed) {
-        out_packed[static_cast<size_t>(q) * k_out + j] = PackedCand{b.key, xn, b.id};
-      } else {
-        out_ids[static_cast<size_t>(q) * k_out + j] = b.id;
-      }
+      s_key[w][j] = ordered_to_f32(wk);
+      s_id[w][j] = wid;
+      s_pos[w][j] = wpos;
+    }
+    n_found = j + 1;
+    if (mine) scan(wk, wid, bk, bid, bpos);                     // (duplicates of the pick rescan too)
+  }
+  __syncwarp();
+
+  // per-pick outputs, in parallel over the picks: |x|^2 gather, ids, packed records / peer buffers
+  for (int j = lane; j < n_found; j += 32) {
+    const int64_t id = s_id[w][j];
+    const int pos = s_pos[w][j];
+    float xn = 0.f;
+    if (LOCAL) {
+      if (bank_xn2) xn = bank_xn2[id - id_offset];
+    } else {
+      const int p = pos / k_in, sidx = pos - p * k_in;
+      const size_t a = (static_cast<size_t>(p) * nq + q) * k_in + sidx;
+      if (cand_packed) xn = cand_packed[a].xn2;
+      else if (cand_xn2) xn = cand_xn2[a];
+    }
+    s_xn2[w][j] = xn;
+    const size_t o = static_cast<size_t>(q) * k_out + j;
+    if (LOCAL && xo.n_peers > 0) {
+      const PackedCand rec{s_key[w][j], xn, id};
+      for (int g = 0; g < xo.n_peers; ++g) xo.bufs[g][o] = rec;
+    } else if (LOCAL && out_packed) {
+      out_packed[o] = PackedCand{s_key[w][j], xn, id};
+    } else {
+      out_ids[o] = id;
     }
   }
   __syncwarp();

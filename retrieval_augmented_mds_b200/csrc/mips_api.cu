@@ -92,6 +92,9 @@ struct mips_index_s {
   float* part_key = nullptr;   size_t part_key_bytes = 0;
   int* part_ids = nullptr;     size_t part_ids_bytes = 0;
   int* ign_local = nullptr;    size_t ign_bytes = 0;
+  int* after_row = nullptr;    size_t after_row_bytes = 0;  // multi-pass bound as shard-local rows
+  float* hafter_key = nullptr; size_t hafter_key_bytes = 0; // mips_search_host, k > MIPS_MAX_K: bound of the next pass
+  int64_t* hafter_id = nullptr; size_t hafter_id_bytes = 0;
   int* pace = nullptr;         size_t pace_bytes = 0;
   uint32_t* pool = nullptr;    size_t pool_bytes = 0;       // pooled admission thresholds [nq_pad, n_splits]
   __nv_bfloat16* q_hi = nullptr; size_t q_hi_bytes = 0;     // bf16-rounded prepared queries
@@ -276,6 +279,7 @@ static int set_kernel_attrs(mips_index_s* h) {
   TC_ATTR(false, 64, 3);  TC_ATTR(false, 64, 12); TC_ATTR(false, 64, 2);
 #undef TC_ATTR
   CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 4 * 8));
+  CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 4 * 8));
 #define TC2_ATTR(L2, K)                                                                        \
   CUDA_TRY(cudaFuncSetAttribute(tc2::search_tc2_kernel<L2, K, false>,                          \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_LIMIT)); \
@@ -341,7 +345,7 @@ int mips_destroy(mips_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* dev[] = {h->bank, h->norm2, h->max_norm2_bits, h->q_prep, h->q_norm2, h->part_key,
-                 h->part_ids, h->ign_local, h->pace, h->pool, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->sh_local, h->sh_gath, h->sh_qn2, h->dp_q, h->dp_ign, h->hq, h->hign, h->hkey, h->hids,
+                 h->part_ids, h->ign_local, h->after_row, h->hafter_key, h->hafter_id, h->pace, h->pool, h->shadow, h->q_hi, h->q_res2, h->cand_key, h->cand_rows, h->fb_flags, h->stage_x, h->sh_local, h->sh_gath, h->sh_qn2, h->dp_q, h->dp_ign, h->hq, h->hign, h->hkey, h->hids,
                  h->hxn2, h->hqn2, h->hD, h->hI};
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -588,7 +592,7 @@ int mips_reconstruct(mips_handle h, int64_t row0, int64_t n, float* out, int out
 // the bf16 shadow of an fp32 bank). Leaves [n_splits, nq, k] candidate lists in h->part_key / part_ids.
 static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_bfloat16* q_bf16, int nq,
                       int nq_pad, int k, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out,
-                      bool allow_pool = true) {
+                      bool allow_pool = true, const float* after_key = nullptr, const int* after_row = nullptr) {
     int rc = encode_query_tmap(h, q_bf16, nq_pad);
     if (rc) return rc;
     const int n_tiles = static_cast<int>((h->ntotal + tc2::TILE_N - 1) / tc2::TILE_N);
@@ -604,6 +608,8 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
     p.q = q_bf16;
     p.xnorm2 = h->norm2;
     p.ignore_local = ign_local;
+    p.after_key = after_key;
+    p.after_row = after_row;
     p.part_key = h->part_key;
     p.part_ids = h->part_ids;
     p.ntotal = h->ntotal;
@@ -672,7 +678,8 @@ static int launch_tc2(mips_index_s* h, const CUtensorMap& tmap_bank, const __nv_
 // K1, 1-CTA tensor-core kernel over a bf16 row matrix described by `tmap` (boxes of acc_n rows): the bf16 bank,
 // or the bf16 shadow of an fp32 bank. Leaves [n_splits, nq, k] candidate sets in h->part_key / part_ids.
 static int launch_tc(mips_index_s* h, const CUtensorMap& tmap, const __nv_bfloat16* q_bf16, int nq, int nq_pad, int k,
-                     int acc_n, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out) {
+                     int acc_n, const int* ign_local, bool l2, cudaStream_t st, int* n_parts_out,
+                     const float* after_key = nullptr, const int* after_row = nullptr) {
     const int n_tiles = static_cast<int>((h->ntotal + acc_n - 1) / acc_n);
     const int n_qtiles = nq_pad / tc::BLOCK_M;
     int n_splits = std::max(1, std::min(h->sm_count / n_qtiles, n_tiles));
@@ -686,6 +693,8 @@ static int launch_tc(mips_index_s* h, const CUtensorMap& tmap, const __nv_bfloat
     p.q = q_bf16;
     p.xnorm2 = h->norm2;
     p.ignore_local = ign_local;
+    p.after_key = after_key;
+    p.after_row = after_row;
     p.part_key = h->part_key;
     p.part_ids = h->part_ids;
     p.ntotal = h->ntotal;
@@ -726,7 +735,8 @@ static int launch_tc(mips_index_s* h, const CUtensorMap& tmap, const __nv_bfloat
 // K1, exact fp32-FMA kernel over the stored rows (any dtype). `tile_active` (device, one int per
 // 64-query tile, or null) restricts the launch to the query tiles that need recomputing.
 static int launch_simt(mips_index_s* h, int nq, int k, const int* ign_local, bool l2, const int* tile_active,
-                       cudaStream_t st, int* n_parts_out) {
+                       cudaStream_t st, int* n_parts_out, const float* after_key = nullptr,
+                       const int* after_row = nullptr) {
   const int n_tiles = static_cast<int>((h->ntotal + simt::BN - 1) / simt::BN);
   const int n_qtiles = (nq + simt::BM - 1) / simt::BM;
   const int target_blocks = 4 * h->sm_count;
@@ -745,7 +755,7 @@ static int launch_simt(mips_index_s* h, int nq, int k, const int* ign_local, boo
 #define SIMT_LAUNCH(T, L2)                                                                         \
   simt::search_simt_kernel<T, L2><<<grid, simt::THREADS, smem, st>>>(                              \
       static_cast<const T*>(h->q_prep), static_cast<const T*>(h->bank), h->norm2, nq, h->ntotal,   \
-      h->d_pad, k, ign_local, n_tiles, h->part_key, h->part_ids, tile_active)
+      h->d_pad, k, ign_local, n_tiles, h->part_key, h->part_ids, tile_active, after_key, after_row)
   if (h->dtype == MIPS_DTYPE_BF16) {
     if (l2) SIMT_LAUNCH(__nv_bfloat16, true); else SIMT_LAUNCH(__nv_bfloat16, false);
   } else {
@@ -763,8 +773,10 @@ static int launch_merge_local(mips_index_s* h, const float* part_key, const int*
                               int64_t* out_ids, float* out_xn2, void* out_packed, const int* q_active,
                               cudaStream_t st, const char* what, const XchgOut* xo = nullptr) {
   const int C = n_parts * k_in;
-  int cap = 0, wpb = 4;   // queries (warps) per block: fewer when one query's candidates need a large staging area
-  if (C > 64 && C <= 6144) cap = C;
+  // every query's candidates are staged in shared memory (8 bytes each); fewer queries (warps) per block when
+  // one query needs a large staging area
+  int cap = 0, wpb = 4;
+  if (C > 0 && C <= 6144) cap = C;
   else if (C > 6144 && C <= 12288) { cap = C; wpb = 2; }
   else if (C > 12288 && C <= 24576) { cap = C; wpb = 1; }
   const size_t smem = static_cast<size_t>(wpb) * cap * sizeof(uint2);
@@ -786,7 +798,8 @@ static int tcx_split_list(int k) { return std::max(k, 16); }
 static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_normalize,
                         const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
                         int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
-                        cudaStream_t st, const XchgOut* xo = nullptr) {
+                        cudaStream_t st, const XchgOut* xo = nullptr, const float* after_key = nullptr,
+                        const int64_t* after_id = nullptr) {
   int rc;
   const size_t eb = elem_bytes(h);
   const int nq_pad = round_up_i(nq, (algo == MIPS_ALGO_TC2 || algo == MIPS_ALGO_TCX) ? tc2::PAIR_M : tc::BLOCK_M);
@@ -808,6 +821,15 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
                                                              h->ign_local);
     LAUNCH_CHECK("ignore_to_local_kernel");
     ign_local = h->ign_local;
+  }
+
+  const int* after_row = nullptr;
+  if (after_key) {
+    rc = grow(&h->after_row, &h->after_row_bytes, static_cast<size_t>(nq) * sizeof(int));
+    if (rc) return rc;
+    bound_to_local_kernel<<<(nq + 255) / 256, 256, 0, st>>>(after_id, nq, id_offset, h->after_row);
+    LAUNCH_CHECK("bound_to_local_kernel");
+    after_row = h->after_row;
   }
 
   const bool l2 = h->metric == MIPS_METRIC_L2;
@@ -866,17 +888,18 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     return 0;
   }
   if (algo == MIPS_ALGO_TC2) {
-    rc = launch_tc2(h, h->tmap64, static_cast<const __nv_bfloat16*>(h->q_prep), nq, nq_pad, k, ign_local, l2, st, &n_parts);
+    rc = launch_tc2(h, h->tmap64, static_cast<const __nv_bfloat16*>(h->q_prep), nq, nq_pad, k, ign_local, l2, st, &n_parts,
+                    true, after_key, after_row);
     if (rc) return rc;
     h->last_algo = "tc2";
   } else if (use_tc) {
     const int acc_n = algo == MIPS_ALGO_TC128 ? 128 : 64;
     rc = launch_tc(h, acc_n == 128 ? h->tmap128 : h->tmap64, static_cast<const __nv_bfloat16*>(h->q_prep), nq, nq_pad, k,
-                   acc_n, ign_local, l2, st, &n_parts);
+                   acc_n, ign_local, l2, st, &n_parts, after_key, after_row);
     if (rc) return rc;
     h->last_algo = acc_n == 128 ? "tc128" : "tc";
   } else {
-    rc = launch_simt(h, nq, k, ign_local, l2, nullptr, st, &n_parts);
+    rc = launch_simt(h, nq, k, ign_local, l2, nullptr, st, &n_parts, after_key, after_row);
     if (rc) return rc;
     h->last_algo = "simt";
   }
@@ -895,7 +918,8 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
 static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q_normalize,
                              const int64_t* ignore_ids, int64_t id_offset, int algo, float* out_key,
                              int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
-                             void* stream, const XchgOut* xo = nullptr) {
+                             void* stream, const XchgOut* xo = nullptr, const float* after_key = nullptr,
+                             const int64_t* after_id = nullptr) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
   if (nq < 0 || (nq > 0 && (!q || (!xo && !out_packed && (!out_key || !out_ids)))))
     return set_err(MIPS_E_INVALID, "bad q / outputs");
@@ -908,10 +932,14 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
                       tc2::pick_stages(h->d_pad, k, 2) >= 2;
   const bool tcx_ok = h->dtype == MIPS_DTYPE_F32 && h->shadow_valid &&
                       tc2::pick_stages(h->d_pad, tcx_split_list(k), 2) >= 2;
+  if ((after_key == nullptr) != (after_id == nullptr)) return set_err(MIPS_E_INVALID, "after_key and after_id go together");
   if (algo == MIPS_ALGO_AUTO && h->dtype == MIPS_DTYPE_F32) {
     static const int auto_tcx = env_int("MIPS_AUTO_TCX", 1);
-    algo = (tcx_ok && auto_tcx) ? MIPS_ALGO_TCX : MIPS_ALGO_SIMT;
+    // a bounded pass (multi-pass search, k > MIPS_MAX_K) compares EXACT keys: the fp32 FMA kernel, not the filter
+    algo = (tcx_ok && auto_tcx && !after_key) ? MIPS_ALGO_TCX : MIPS_ALGO_SIMT;
   }
+  if (algo == MIPS_ALGO_TCX && after_key)
+    return set_err(MIPS_E_UNSUPPORTED, "bounded passes on an fp32 bank run on the exact fp32 kernel (algo auto / simt)");
   if (algo == MIPS_ALGO_TCX && !tcx_ok)
     return set_err(MIPS_E_UNSUPPORTED, "exact tensor-core search needs an fp32 bank with d_pad <= %d (and k small enough for shared memory)", tc2::MAX_KCH * tc2::KCH);
   if (algo == MIPS_ALGO_AUTO) {
@@ -948,7 +976,7 @@ static int search_local_impl(mips_handle h, const float* q, int nq, int k, int q
                           out_xnorm2 ? out_xnorm2 + static_cast<size_t>(q0) * k : nullptr,
                           out_qnorm2 ? out_qnorm2 + q0 : nullptr,
                           out_packed ? static_cast<PackedCand*>(out_packed) + static_cast<size_t>(q0) * k : nullptr,
-                          st, xo);
+                          st, xo, after_key ? after_key + q0 : nullptr, after_id ? after_id + q0 : nullptr);
     if (rc) return rc;
   }
   return 0;
@@ -961,6 +989,14 @@ int mips_search_local(mips_handle h, const float* q, int nq, int k, int q_normal
                            out_xnorm2, out_qnorm2, nullptr, stream);
 }
 
+int mips_search_local_after(mips_handle h, const float* q, int nq, int k, int q_normalize, const int64_t* ignore_ids,
+                            int64_t id_offset, int algo, const float* after_key, const int64_t* after_id,
+                            float* out_key, int64_t* out_ids, float* out_xnorm2, float* out_qnorm2, void* out_packed,
+                            void* stream) {
+  return search_local_impl(h, q, nq, k, q_normalize, ignore_ids, id_offset, algo, out_key, out_ids, out_xnorm2,
+                           out_qnorm2, out_packed, stream, nullptr, after_key, after_id);
+}
+
 int mips_search_local_packed(mips_handle h, const float* q, int nq, int k, int q_normalize,
                              const int64_t* ignore_ids, int64_t id_offset, int algo, void* out_packed,
                              float* out_qnorm2, void* stream) {
@@ -970,6 +1006,17 @@ int mips_search_local_packed(mips_handle h, const float* q, int nq, int k, int q
 }
 
 // ------------------------------------------------------------------------------------------ K2
+// FINAL merge: candidates of a query staged in shared memory (16 bytes each: key, position, int64 id)
+static int final_merge_staging(int C, int* cap, int* wpb) {
+  *cap = 0;
+  *wpb = 4;
+  if (C > 0 && C <= 3072) *cap = C;
+  else if (C > 3072 && C <= 12288) { *cap = C; *wpb = 1; }
+  if (static_cast<size_t>(*wpb) * *cap * 16 > 48 * 1024)   // opt-in per device; this entry point has no handle
+    CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 4 * 8));
+  return 0;
+}
+
 static int merge_impl(const float* cand_key, const int64_t* cand_ids, const float* cand_xnorm2,
                       const void* cand_packed, int n_parts,
                int nq, int k_in, int k_out, int metric, int out_mode, float phi, const float* q_norm2,
@@ -987,10 +1034,13 @@ static int merge_impl(const float* cand_key, const int64_t* cand_ids, const floa
     return set_err(MIPS_E_INVALID, "q_norm2 required for L2 / cosine outputs");
   if (memory_bias && mem_len < 1) return set_err(MIPS_E_INVALID, "mem_len must be >= 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  merge_topk_kernel<false><<<(nq + 3) / 4, 128, 0, st>>>(
+  int cap, wpb;
+  int rc_st = final_merge_staging(n_parts * k_in, &cap, &wpb);
+  if (rc_st) return rc_st;
+  merge_topk_kernel<false><<<(nq + wpb - 1) / wpb, 32 * wpb, static_cast<size_t>(wpb) * cap * 16, st>>>(
       cand_key, cand_ids, cand_xnorm2, nullptr, n_parts, nq, k_in, k_out, 0, ignore_ids, metric, out_mode,
       phi, q_norm2, D, I, nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len,
-      static_cast<const PackedCand*>(cand_packed), nullptr);
+      static_cast<const PackedCand*>(cand_packed), nullptr, nullptr, cap);
   LAUNCH_CHECK("merge_topk_kernel<final>");
   return 0;
 }
@@ -1017,11 +1067,13 @@ int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normal
                      const int64_t* ignore_ids, int out_mode, float* D, int64_t* I, void* stream) {
   if (!h) return set_err(MIPS_E_INVALID, "null handle");
   if (nq < 0 || (nq > 0 && (!xq || !D || !I))) return set_err(MIPS_E_INVALID, "bad host buffers");
-  if (k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "k must be in [1, %d], got %d", MIPS_MAX_K, k);
+  if (k < 1 || k > MIPS_MAX_K_MULTIPASS)
+    return set_err(MIPS_E_INVALID, "k must be in [1, %d], got %d", MIPS_MAX_K_MULTIPASS, k);
   if (nq == 0) return 0;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t nk = static_cast<size_t>(nq) * k;
+  const int kp_max = std::min(k, MIPS_MAX_K);                 // results per pass
+  const size_t nk = static_cast<size_t>(nq) * kp_max;
   int rc = 0;
   if ((rc = grow(&h->hq, &h->hq_bytes, static_cast<size_t>(nq) * h->d * sizeof(float)))) return rc;
   if ((rc = grow(&h->hkey, &h->hkey_bytes, nk * sizeof(float)))) return rc;
@@ -1030,6 +1082,10 @@ int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normal
   if ((rc = grow(&h->hqn2, &h->hqn2_bytes, static_cast<size_t>(nq) * sizeof(float)))) return rc;
   if ((rc = grow(&h->hD, &h->hD_bytes, nk * sizeof(float)))) return rc;
   if ((rc = grow(&h->hI, &h->hI_bytes, nk * sizeof(int64_t)))) return rc;
+  if (k > MIPS_MAX_K) {
+    if ((rc = grow(&h->hafter_key, &h->hafter_key_bytes, static_cast<size_t>(nq) * sizeof(float)))) return rc;
+    if ((rc = grow(&h->hafter_id, &h->hafter_id_bytes, static_cast<size_t>(nq) * sizeof(int64_t)))) return rc;
+  }
   CUDA_TRY(cudaMemcpyAsync(h->hq, xq, static_cast<size_t>(nq) * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
   const int64_t* ign_dev = nullptr;
   if (ignore_ids) {
@@ -1037,14 +1093,32 @@ int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normal
     CUDA_TRY(cudaMemcpyAsync(h->hign, ignore_ids, static_cast<size_t>(nq) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     ign_dev = h->hign;
   }
-  rc = mips_search_local(h, h->hq, nq, k, q_normalize, ign_dev, 0, MIPS_ALGO_AUTO, h->hkey, h->hids,
-                         h->hxn2, h->hqn2, st);
-  if (rc) return rc;
-  rc = mips_merge(h->hkey, h->hids, h->hxn2, 1, nq, k, k, h->metric, out_mode, h->phi, h->hqn2, nullptr,
-                  h->hD, h->hI, nullptr, nullptr, 1.f, 0.f, nullptr, 0, st);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(D, h->hD, nk * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(I, h->hI, nk * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  // k <= MIPS_MAX_K: one pass. Larger k (faiss accepts any k; the reference asks for k + 1 with an ignore list,
+  // mips.py:383-386): passes of MIPS_MAX_K results, each restricted to the rows strictly after the last result
+  // of the pass before in the order (key descending, id ascending) — exact, and a pass costs one search.
+  // the bound compares keys for EQUALITY across passes: every pass must compute a row's key with the same
+  // arithmetic. The tensor kernels do (same tiles, same accumulation order); an fp32 bank's first pass would be
+  // the filter + re-rank path, whose keys differ in the last bits from the fp32 FMA kernel of the bounded passes
+  const int algo = (k > MIPS_MAX_K && h->dtype == MIPS_DTYPE_F32) ? MIPS_ALGO_SIMT : MIPS_ALGO_AUTO;
+  for (int done = 0; done < k; done += MIPS_MAX_K) {
+    const int kp = std::min(MIPS_MAX_K, k - done);
+    rc = mips_search_local_after(h, h->hq, nq, kp, q_normalize, ign_dev, 0, algo,
+                                 done ? h->hafter_key : nullptr, done ? h->hafter_id : nullptr, h->hkey, h->hids,
+                                 h->hxn2, h->hqn2, nullptr, st);
+    if (rc) return rc;
+    rc = mips_merge(h->hkey, h->hids, h->hxn2, 1, nq, kp, kp, h->metric, out_mode, h->phi, h->hqn2, nullptr,
+                    h->hD, h->hI, nullptr, nullptr, 1.f, 0.f, nullptr, 0, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(D + done, static_cast<size_t>(k) * sizeof(float), h->hD, static_cast<size_t>(kp) * sizeof(float),
+                               static_cast<size_t>(kp) * sizeof(float), nq, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpy2DAsync(I + done, static_cast<size_t>(k) * sizeof(int64_t), h->hI,
+                               static_cast<size_t>(kp) * sizeof(int64_t), static_cast<size_t>(kp) * sizeof(int64_t), nq,
+                               cudaMemcpyDeviceToHost, st));
+    if (done + kp < k) {
+      take_last_kernel<<<(nq + 255) / 256, 256, 0, st>>>(h->hkey, h->hids, nq, kp, h->hafter_key, h->hafter_id);
+      LAUNCH_CHECK("take_last_kernel");
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1164,10 +1238,14 @@ int mips_merge_xchg(const void* my_buf, const uint32_t* my_flags, int n_ranks, u
     return set_err(MIPS_E_INVALID, "q_norm2 required for L2 / cosine outputs");
   if (memory_bias && mem_len < 1) return set_err(MIPS_E_INVALID, "mem_len must be >= 1");
   static const int xchg_timeout_s = env_int("MIPS_XCHG_TIMEOUT_S", 120);
-  merge_topk_kernel<false><<<(nq + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  int cap, wpb;
+  int rc_st = final_merge_staging(n_ranks * k_in, &cap, &wpb);
+  if (rc_st) return rc_st;
+  merge_topk_kernel<false><<<(nq + wpb - 1) / wpb, 32 * wpb, static_cast<size_t>(wpb) * cap * 16,
+                             static_cast<cudaStream_t>(stream)>>>(
       nullptr, nullptr, nullptr, nullptr, n_ranks, nq, k_in, k_out, 0, ignore_ids, metric, out_mode, phi, q_norm2, D, I,
       nullptr, cosine, doc_prob, beta, beta_bias, memory_bias, mem_len, static_cast<const PackedCand*>(my_buf), nullptr,
-      nullptr, 0, XchgOut{nullptr, nullptr, nullptr, 0u, 0},
+      nullptr, cap, XchgOut{nullptr, nullptr, nullptr, 0u, 0},
       XchgIn{my_flags, seq, n_ranks, const_cast<uint32_t*>(my_flags) + MIPS_XCHG_TIMEOUT_WORD,
              static_cast<unsigned long long>(std::max(1, xchg_timeout_s)) * 1000000000ull});
   LAUNCH_CHECK("merge_topk_kernel<final, peer exchange>");

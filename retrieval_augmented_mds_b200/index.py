@@ -15,8 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2, ALGO_TCX, DTYPE_BF16, DTYPE_F32, MAX_K, OUT_AUGL2, OUT_IP,
-                   OUT_L2, check)
+from ._lib import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC128, ALGO_TC2, ALGO_TCX, DTYPE_BF16, DTYPE_F32, MAX_K, MAX_K_MULTIPASS,
+                   OUT_AUGL2, OUT_IP, OUT_L2, check)
 
 METRIC_INNER_PRODUCT = 0  # faiss.METRIC_INNER_PRODUCT
 METRIC_L2 = 1  # faiss.METRIC_L2
@@ -161,10 +161,13 @@ class B200FlatIndex:
         return out.view(*ids.shape, self.d)
 
     # ------------------------------------------------------------------ search side
-    def _check_k(self, k: int) -> int:
+    def _check_k(self, k: int, multipass: bool = False) -> int:
+        """One search pass keeps up to MAX_K (64) results per query; the public search calls accept up to
+        MAX_K_MULTIPASS by running bounded passes (faiss accepts any k: mips.py:383-386)."""
         k = int(k)
-        if k < 1 or k > MAX_K:
-            raise ValueError(f"k must be in [1, {MAX_K}], got {k}")
+        top = MAX_K_MULTIPASS if multipass else MAX_K
+        if k < 1 or k > top:
+            raise ValueError(f"k must be in [1, {top}], got {k}")
         return k
 
     def search(self, xq, k: int, return_torch: bool = False):
@@ -172,7 +175,7 @@ class B200FlatIndex:
         L2 squared distances ascending, -1 padding. numpy in -> numpy out through the host entry
         point (H2D + kernels + D2H in one C call); CUDA tensor in (or return_torch=True) keeps
         everything on the device (removes the round trip of retriever_generator.py:143)."""
-        k = self._check_k(k)
+        k = self._check_k(k, multipass=True)
         if isinstance(xq, torch.Tensor) and (xq.is_cuda or return_torch):
             r = self.search_ex(xq, k)
             return r["scores"], r["ids"]
@@ -201,8 +204,9 @@ class B200FlatIndex:
                     D: Optional[np.ndarray] = None, I: Optional[np.ndarray] = None):
         """The reference-facing end-to-end call (host buffers in and out, one C-ABI call):
         Mips.search semantics incl. the per-query ignored id (mips.py:382-400). ids are local
-        (id_offset is not applied). D / I may be preallocated (e.g. pinned) arrays."""
-        k = self._check_k(k)
+        (id_offset is not applied). D / I may be preallocated (e.g. pinned) arrays. k > 64 runs bounded
+        passes inside the C call."""
+        k = self._check_k(k, multipass=True)
         xq = np.ascontiguousarray(xq, dtype=np.float32)
         if xq.ndim != 2 or xq.shape[1] != self.d:
             raise ValueError(f"Shape of query must be [nq, {self.d}], got {xq.shape}")
@@ -225,9 +229,11 @@ class B200FlatIndex:
         return D, I
 
     def search_local(self, xq: torch.Tensor, k: int, ignore_ids: Optional[torch.Tensor] = None,
-                     normalize_queries: bool = False, algo: str = "auto"):
+                     normalize_queries: bool = False, algo: str = "auto", after=None):
         """K1 + local merge on this shard: returns device tensors
-        (key [nq,k] descending ranking key, ids [nq,k] GLOBAL int64, xnorm2 [nq,k], qnorm2 [nq])."""
+        (key [nq,k] descending ranking key, ids [nq,k] GLOBAL int64, xnorm2 [nq,k], qnorm2 [nq]).
+        after = (key [nq], id [nq]): one pass of a multi-pass search — only rows strictly after that
+        (key, id) in the order (key descending, id ascending) are eligible (mips_search_local_after)."""
         k = self._check_k(k)
         if not isinstance(xq, torch.Tensor):
             xq = torch.as_tensor(np.ascontiguousarray(xq, dtype=np.float32))
@@ -246,11 +252,33 @@ class B200FlatIndex:
             ign = torch.as_tensor(ignore_ids).to(device=self.device, dtype=torch.int64).contiguous()
             if ign.shape != (nq,):
                 raise ValueError("ignore_ids must have one id per query")
+        a_key = a_id = None
+        if after is not None:
+            a_key = after[0].to(device=self.device, dtype=torch.float32).contiguous()
+            a_id = after[1].to(device=self.device, dtype=torch.int64).contiguous()
         with torch.cuda.device(self.device):
-            check(self._L.mips_search_local(self._h, _ptr(xq), nq, k, int(normalize_queries), _ptr(ign),
-                                            self.id_offset, _ALGOS[algo], _ptr(key), _ptr(ids), _ptr(xn2),
-                                            _ptr(qn2), self._stream()))
+            check(self._L.mips_search_local_after(self._h, _ptr(xq), nq, k, int(normalize_queries), _ptr(ign),
+                                                  self.id_offset, _ALGOS[algo], _ptr(a_key), _ptr(a_id), _ptr(key),
+                                                  _ptr(ids), _ptr(xn2), _ptr(qn2), None, self._stream()))
         return key, ids, xn2, qn2
+
+    def search_local_multipass(self, xq: torch.Tensor, k: int, ignore_ids: Optional[torch.Tensor] = None,
+                               normalize_queries: bool = False, algo: str = "auto"):
+        """search_local for any k <= MAX_K_MULTIPASS: passes of MAX_K results, each bounded by the last result of
+        the pass before (exact: the concatenation is the shard's top-k in (key desc, id asc) order)."""
+        k = self._check_k(k, multipass=True)
+        if self.dtype == "fp32" and algo == "auto" and k > MAX_K:
+            algo = "simt"        # the bound compares keys for equality: every pass on the same (exact fp32) kernel
+        keys, idss, xn2s, qn2, after = [], [], [], None, None
+        for done in range(0, k, MAX_K):
+            kp = min(MAX_K, k - done)
+            key, ids, xn2, qn2 = self.search_local(xq, kp, ignore_ids=ignore_ids, normalize_queries=normalize_queries,
+                                                   algo=algo, after=after)
+            keys.append(key), idss.append(ids), xn2s.append(xn2)
+            last_id = ids[:, -1]
+            after = (torch.where(last_id < 0, torch.full_like(key[:, -1], float("-inf")), key[:, -1]),
+                     torch.where(last_id < 0, torch.full_like(last_id, torch.iinfo(torch.int64).max), last_id))
+        return torch.cat(keys, 1), torch.cat(idss, 1), torch.cat(xn2s, 1), qn2
 
     def search_local_packed(self, xq: torch.Tensor, k: int, ignore_ids: Optional[torch.Tensor] = None,
                             normalize_queries: bool = False, algo: str = "auto"):
@@ -298,7 +326,12 @@ class B200FlatIndex:
                   L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
                   beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> dict:
         """Device-resident search with optional fused outputs. want ⊆ {"scores","ids","cosine",
-        "doc_prob","memory_bias"}; L = memory_seq_len for memory_bias."""
+        "doc_prob","memory_bias"}; L = memory_seq_len for memory_bias. k > 64: bounded passes, outputs from
+        the same arithmetic spelled with tensor ops (finalize_lists; a rare path)."""
+        if int(k) > MAX_K:
+            key, ids, xn2, qn2 = self.search_local_multipass(xq, k, ignore_ids=ignore_ids,
+                                                             normalize_queries=normalize_queries, algo=algo)
+            return finalize_lists(key, ids, xn2, qn2, self.metric_type, out_mode, self.phi, want, L, beta, beta_bias)
         key, ids, xn2, qn2 = self.search_local(xq, k, ignore_ids=ignore_ids,
                                                normalize_queries=normalize_queries, algo=algo)
         return self.merge(key.unsqueeze(0), ids.unsqueeze(0), xn2.unsqueeze(0), qn2, k, want=want,
@@ -329,6 +362,37 @@ class B200FlatIndex:
         """Exact tensor-core search ("tcx", fp32 banks): how many queries failed the exactness
         certificate since the last reset and were recomputed by the exact SIMT kernel."""
         return int(self._L.mips_fallback_queries(self._h, int(reset)))
+
+
+def finalize_lists(key, ids, xn2, qn2, metric_type: int, out_mode, phi: float, want, L, beta: float,
+                   beta_bias: float) -> dict:
+    """The output transform of the merge kernel (k2_merge.cuh, FINAL mode) for result lists longer than one kernel
+    pass holds (k > 64, multi-pass searches): ranking key -> inner product -> D per out_mode, cosine doc scores
+    (retriever_generator.py:159-172), per-doc softmax, memory_bias (:188-192). [nq, k] elementwise tensor ops."""
+    want = set(want)
+    if out_mode is None:
+        out_mode = OUT_IP if metric_type == METRIC_INNER_PRODUCT else OUT_L2
+    valid = ids >= 0
+    ip = key + 0.5 * xn2 if metric_type == METRIC_L2 else key
+    q2 = qn2[:, None]
+    if out_mode == OUT_IP:
+        D = torch.where(valid, ip, torch.full_like(ip, float("-inf")))
+    else:
+        dist_ = torch.clamp(q2 + xn2 - 2.0 * ip, min=0.0) if out_mode == OUT_L2 else q2 + float(phi) - 2.0 * ip
+        D = torch.where(valid, dist_, torch.full_like(ip, float("inf")))
+    out = {"scores": D, "ids": ids}
+    if want & {"cosine", "doc_prob", "memory_bias"}:
+        den = torch.sqrt(q2) * torch.sqrt(xn2)
+        cos = torch.where(valid & (den > 0), ip / den.clamp_min(1e-38), torch.zeros_like(ip))
+        out["cosine"] = cos
+        if "doc_prob" in want:
+            z = torch.where(valid, beta * cos + beta_bias, torch.full_like(cos, float("-inf")))
+            out["doc_prob"] = torch.nan_to_num(torch.softmax(z, dim=1), nan=0.0)
+        if "memory_bias" in want:
+            if not L or L < 1:
+                raise ValueError("memory_bias needs L (memory_seq_len) >= 1")
+            out["memory_bias"] = torch.where(valid, cos, torch.zeros_like(cos)).repeat_interleave(int(L), dim=1)
+    return out
 
 
 def alloc_outputs(dev, nq: int, k: int, want, L) -> dict:

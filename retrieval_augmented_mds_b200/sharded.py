@@ -332,11 +332,47 @@ class ShardedFlatIndex:
         return _index.sharded_step(self.local, comm, self.world, self.rank, dp, xq, ign, k, out, L,
                                    normalize_queries, out_mode, beta, beta_bias, algo)
 
+    # ------------------------------------------------------------------ k > 64 (rare: bounded passes per shard)
+    def _search_big_k(self, dp: bool, xq, k, ignore_ids, want, L, normalize_queries, out_mode, beta, beta_bias, algo):
+        """k > 64: every shard runs its bounded passes (B200FlatIndex.search_local_multipass), the [nq, k] lists
+        travel through torch.distributed and are merged by (key desc, id asc) with two stable sorts."""
+        xq, ign = self._prep(xq, ignore_ids)
+        B = xq.shape[0]
+        if dp and self.world > 1:
+            q_all = torch.empty((self.world * B, xq.shape[1]), dtype=torch.float32, device=xq.device)
+            dist.all_gather_into_tensor(q_all, xq, group=self.group)
+            if ign is not None:
+                ign_all = torch.empty((self.world * B,), dtype=torch.int64, device=xq.device)
+                dist.all_gather_into_tensor(ign_all, ign, group=self.group)
+                ign = ign_all
+            xq = q_all
+        key, ids, xn2, qn2 = self.local.search_local_multipass(xq, k, ignore_ids=ign, normalize_queries=normalize_queries,
+                                                               algo=algo)
+        if self.world > 1:
+            nq = xq.shape[0]
+            packed = torch.stack([key.double(), xn2.double(), ids.double()], 0)      # ids < 2^53: exact in fp64
+            allp = torch.empty((self.world,) + tuple(packed.shape), dtype=torch.float64, device=xq.device)
+            dist.all_gather_into_tensor(allp, packed, group=self.group)
+            ck = allp[:, 0].permute(1, 0, 2).reshape(nq, -1).float()
+            cx = allp[:, 1].permute(1, 0, 2).reshape(nq, -1).float()
+            ci = allp[:, 2].permute(1, 0, 2).reshape(nq, -1).long()
+            o1 = torch.sort(torch.where(ci < 0, torch.full_like(ci, torch.iinfo(torch.int64).max), ci), dim=1, stable=True)[1]
+            ck, cx, ci = ck.gather(1, o1), cx.gather(1, o1), ci.gather(1, o1)
+            o2 = torch.sort(ck, dim=1, descending=True, stable=True)[1][:, :k]
+            key, xn2, ids = ck.gather(1, o2), cx.gather(1, o2), ci.gather(1, o2)
+            if dp:
+                mine = slice(self.rank * B, (self.rank + 1) * B)
+                key, xn2, ids, qn2 = key[mine], xn2[mine], ids[mine], qn2[mine]
+        return _index.finalize_lists(key, ids, xn2, qn2, self.local.metric_type, out_mode, self.local.phi, want, L, beta,
+                                     beta_bias)
+
     # ------------------------------------------------------------------ replicated queries
     def search(self, xq, k: int, ignore_ids=None, want: Iterable[str] = ("scores", "ids"),
                L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
                beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> dict:
-        k = self.local._check_k(k)
+        k = self.local._check_k(k, multipass=True)
+        if k > _lib.MAX_K:
+            return self._search_big_k(False, xq, k, ignore_ids, want, L, normalize_queries, out_mode, beta, beta_bias, algo)
         if self.exchange == "p2p" and self.world > 1 and self.local.dtype == "bf16":
             r = self._search_p2p(xq, k, ignore_ids, set(want), L, normalize_queries, out_mode, beta, beta_bias, algo)
             if r is not None:
@@ -359,7 +395,10 @@ class ShardedFlatIndex:
         none) and receives the global top-k of its own queries: all-gather queries -> one local search of
         G*B queries -> all-to-all of 16-byte records -> per-rank merge with the fused doc outputs
         (SURVEY §8e "DP-training variant"). Collective."""
-        k = self.local._check_k(k)
+        k = self.local._check_k(k, multipass=True)
+        if k > _lib.MAX_K:
+            return self._search_big_k(True, xq_local, k, ignore_ids, want, L, normalize_queries, out_mode, beta, beta_bias,
+                                      algo)
         xq, ign = self._prep(xq_local, ignore_ids)
         B = xq.shape[0]
         if self.exchange in ("native", "p2p") or self.world == 1:

@@ -78,3 +78,28 @@ def test_faiss_stand_in_exports_what_the_reference_and_datasets_touch():
         faiss.index_cpu_to_all_gpus(None)
     with pytest.raises(ValueError, match="Flat"):
         faiss.index_factory(8, "IVF100,SQ8", 0)      # approximate factories are rejected before any GPU work
+
+
+def test_flat_files_interchange_with_a_real_faiss(tmp_path):
+    """N4 against the real thing where it exists: a file written by faiss.write_index is read by faiss_io and a
+    file written by faiss_io is read by faiss.read_index (IndexFlatIP and IndexFlatL2). faiss-cpu is not
+    installable in the build image (no network): the test runs wherever a genuine faiss is importable."""
+    faiss = pytest.importorskip("faiss")
+    if "b200" in getattr(faiss, "__version__", ""):
+        pytest.skip("only the stand-in faiss is importable")
+    from retrieval_augmented_mds_b200 import faiss_io
+    rng = np.random.default_rng(0)
+    xb = rng.standard_normal((257, 24), dtype=np.float32)
+    for metric, cls in ((0, faiss.IndexFlatIP), (1, faiss.IndexFlatL2)):
+        index = cls(24)
+        index.add(xb)
+        path = str(tmp_path / f"real_{metric}.faiss")
+        faiss.write_index(index, path)
+        data = open(path, "rb").read()
+        assert data == faiss_io.serialize_rows(xb, metric)                 # byte-identical flat layout
+        ours = str(tmp_path / f"ours_{metric}.faiss")
+        open(ours, "wb").write(faiss_io.serialize_rows(xb, metric))
+        back = faiss.read_index(ours)
+        assert back.ntotal == 257 and back.d == 24 and back.metric_type == metric
+        assert np.array_equal(faiss.vector_to_array(back.get_xb()).reshape(257, 24) if hasattr(back, "get_xb")
+                              else back.reconstruct_n(0, 257), xb)

@@ -89,6 +89,12 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         r = gd.replay(xq_t[mine])
         torch.cuda.synchronize()
         assert np.array_equal(r["ids"].cpu().numpy(), I2[mine])
+        # k > 64 on the sharded bank (bounded passes per shard, lists merged by (key desc, id asc))
+        Dk, Ik = o.exact_topk_f64(xb, xq, 100)
+        r = mp._sharded.search(xq_t, 100, out_mode=0)
+        assert np.array_equal(r["ids"].cpu().numpy(), Ik)
+        r = mp._sharded.search_dp(xq_t[mine], 100, out_mode=0)
+        assert np.array_equal(r["ids"].cpu().numpy(), Ik[mine])
         # a memory refresh keeps the communicator (no new NCCL communicator / exchange buffers per rebuild)
         comm_before = mp._sharded._comm
         mp.begin_refresh(len(rows))

@@ -437,6 +437,42 @@ def test_config2_1m_fp32_planted_neighbours(m):
     torch.testing.assert_close(r["scores"], best_s, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("dtype,nq", [("bf16", 200), ("bf16", 40), ("fp32", 70)])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_k_larger_than_one_pass_multipass_search(m, dtype, nq, metric):
+    """faiss accepts any k (mips.py:383-386 asks for k or k + 1): k > 64 runs bounded passes — each pass only sees
+    rows strictly after the last result of the pass before. Exact against the float64 oracle for every kernel
+    family (CTA pair: nq > 128, 1-CTA: nq <= 128, fp32 bank: exact fp32 kernel), with duplicates straddling the
+    pass boundary, an ignored id per query, k beyond the bank (padding) and the host entry point."""
+    n, d = 3000, 96
+    xb, xq = _data(n, d, nq, seed=77 + nq)
+    xb[1000:1010] = xb[5]            # 11 identical rows: ties that straddle a pass boundary for the planted queries
+    xq[:8] = xb[5] * 3.0
+    if dtype == "bf16":
+        xb, xq = o.bf16_round(xb), o.bf16_round(xq)
+    rtol = RTOL_F32 if dtype == "fp32" else RTOL_BF16
+    ign = np.random.default_rng(1).integers(0, n, nq)
+    ign[:4] = 5                                               # one of the duplicated rows
+    idx = m.B200FlatIndex(d, metric, dtype=dtype)
+    idx.add(xb)
+    for k in (65, 130, 200):
+        D_ref, I_ref = o.exact_topk_f64(xb, xq, k, metric, ignore=ign)
+        r = idx.search_ex(torch.from_numpy(xq), k, ignore_ids=torch.from_numpy(ign), want=("scores", "ids", "cosine"))
+        o.check_topk(xb, xq, r["scores"].cpu().numpy(), r["ids"].cpu().numpy(), metric, rtol=rtol, D_ref=D_ref, I_ref=I_ref,
+                     ignore=ign, what=f"multipass {dtype} k={k}")
+        D, I = idx.search_host(xq, k, ignore_ids=ign)         # the loop inside the C call
+        assert np.array_equal(I, r["ids"].cpu().numpy())
+        got = r["ids"].cpu().numpy()
+        assert all(len(set(row)) == k for row in got)         # no result twice across passes
+    small = m.B200FlatIndex(d, metric, dtype=dtype)
+    small.add(xb[:100])
+    D, I = small.search(xq[:3], 150)                          # k > ntotal: -1 padding after the 100 rows
+    assert (I[:, :100] >= 0).all() and (I[:, 100:] == -1).all()
+    assert np.all(np.isinf(D[:, 100:]))
+    with pytest.raises(ValueError):
+        idx.search(xq, 5000)
+
+
 def _brute_force_same_inputs(idx, xq, k, chunk=500_000):
     """fp32 flat IP over the rows AS STORED (bf16-rounded, up-cast) — the "same inputs" reference of the
     north star — chunked on the GPU; returns (scores, ids) by (score desc, id asc)."""
