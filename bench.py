@@ -334,7 +334,8 @@ def run_ours(args) -> None:
     from retrieval_augmented_mds_b200.sharded import ShardedFlatIndex, balanced_range
 
     import faulthandler
-    faulthandler.dump_traceback_later(1200, exit=True)   # a stuck collective must end the run, not hold the box
+    # a stuck collective must end the run (with the stacks of every thread on stderr), not hold the box
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "600")), exit=True)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -482,7 +483,7 @@ def run_ours(args) -> None:
     if rank == 0 and len(sampler.rows) < 3:      # very short runs: keep the GPU under load until a few samples exist
         t_end = time.perf_counter() + 1.0
         while len(sampler.rows) < 3 and time.perf_counter() < t_end:
-            step_device()
+            idx.search_ex(xq_dev, k, algo=args.algo)     # LOCAL search only: rank 0 is alone in this loop
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     barrier()

@@ -27,8 +27,9 @@ rank = int(os.environ.get("RANK", "0"))
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
 dev = torch.device("cuda", local_rank)
+import faulthandler
+faulthandler.dump_traceback_later(600, exit=True)
 if world > 1:
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=dev)
 rows = balanced_range(N, rank, world)
 gen = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -65,24 +66,44 @@ rebuild()
 sync()
 rebuild_ms = 1e3 * (time.perf_counter() - t0)
 search = (lambda: sh.search(xq, K)) if sh is not None else (lambda: idx.search_ex(xq, K))
-for _ in range(5):
-    out = search()
-sync()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 steps = 50
-e0.record()
-for _ in range(steps):
-    out = search()
-e1.record()
+
+
+def timed(fn):
+    for _ in range(5):
+        fn()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+eager_ms = timed(search)
+idx.set_profiling(True)
+for _ in range(20):
+    search()
 torch.cuda.synchronize()
-t = torch.tensor([e0.elapsed_time(e1) / steps, rebuild_ms], device=dev)
+k1_ms, k1_n = idx.k1_ms_total()
+idx.set_profiling(False)
+g = sh.capture(NQ, K) if sh is not None else idx.capture(NQ, K)      # the whole step as ONE CUDA graph
+g.xq.copy_(xq)
+graph_ms = timed(lambda: g.graph.replay())
+t = torch.tensor([graph_ms, eager_ms, rebuild_ms, k1_ms / max(k1_n, 1)], device=dev)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    ms, rb = float(t[0]), float(t[1])
+    ms, eg, rb, k1 = (float(v) for v in t)
+    bound_ms = 2.0 * NQ * N * D / world / 1686.4e9
     print(json.dumps({"config": f"C5 rebuild {N}x{D} index (device embeddings) + search nq={NQ} k={K}", "n_gpus": world,
-                      "rebuild_ms": rb, "rebuild_rows_per_s": N / rb * 1e3, "search_ms": ms,
-                      "search_qps": NQ / ms * 1e3, "kernel": idx.last_algo,
-                      "search_tflops": 2.0 * NQ * N * D / ms / 1e9}))
+                      "rebuild_ms": rb, "rebuild_rows_per_s": N / rb * 1e3, "search_ms": ms, "search_ms_eager": eg,
+                      "k1_ms": k1, "search_qps": NQ / ms * 1e3, "kernel": idx.last_algo,
+                      "search_tflops": 2.0 * NQ * N * D / ms / 1e9, "tensor_bound_ms": bound_ms,
+                      "frac_of_bound": bound_ms / ms, "step": "one CUDA graph replay (max over ranks)"}))
+if sh is not None:
+    sh.close()
 if world > 1:
     dist.destroy_process_group()
