@@ -385,9 +385,16 @@ def run_ours(args) -> None:
 
     # the timed step: ONE CUDA graph = query prep + K1 + local merge (+ ncclAllGather + final merge)
     use_graph = not args.no_graph and (sh is None or sh.exchange == "native")
+    graph_host = None
     if use_graph:
         graph = sh.capture(nq, k, algo=args.algo) if sh is not None else idx.capture(nq, k, algo=args.algo)
         graph.xq.copy_(xq_dev)
+        if sh is not None and args.e2e_graph_io:
+            # e2e variant: the H2D copy of the queries (pinned host memory) and the D2H copies of (D, I) inside the
+            # graph — one launch per step. Measured at N=2: 6.71 ms per step against 6.53 ms for copies issued
+            # around the graph (memcpy nodes launch slower than the copy engine calls they replace): off by default
+            graph_host = sh.capture(nq, k, algo=args.algo, host_io=True)
+            graph_host.xq_host.copy_(xq_host)
 
     def step_eager():
         if sh is not None:
@@ -407,8 +414,11 @@ def run_ours(args) -> None:
         if sh is None:
             idx.search_host(xq_host.numpy(), k, D=D_pin.numpy(), I=I_pin.numpy())   # one C-ABI call, host in / out
             return
+        if graph_host is not None:
+            graph_host.replay_host()             # H2D + step + D2H in one graph, then synchronize: (D, I) are in the
+            return                               # pinned host tensors graph_host.out_host
         if use_graph:
-            r = graph.replay(xq_host)                                   # H2D from pinned memory + the graph
+            r = graph.replay(xq_host)            # H2D from pinned memory on the step's stream + the graph
         else:
             r = sh.search(xq_host.to(dev, non_blocking=True), k)
         D_pin.copy_(r["scores"], non_blocking=True)
@@ -491,7 +501,8 @@ def run_ours(args) -> None:
     # sanity: the timed path returned a real result (ids valid, scores descending), identical through e2e
     assert int(final_ids.min()) >= 0 and int(final_ids.max()) < n
     assert bool((final_scores[:, :-1] >= final_scores[:, 1:]).all())
-    assert torch.equal(I_pin.to(dev), final_ids), "e2e step and device step disagree"
+    e2e_ids = graph_host.out_host["ids"] if graph_host is not None else I_pin
+    assert torch.equal(e2e_ids.to(dev), final_ids), "e2e step and device step disagree"
 
     # ---- parity of the timed path at this N
     parity = None
@@ -570,6 +581,7 @@ def main() -> None:
     ap.add_argument("--exchange", default=None, choices=["native", "torch", "nccl", "p2p"],
                     help="cross-GPU step: native = raw ncclAllGather issued by the C ABI on the step's stream (default); "
                          "torch = torch.distributed all-gather between C-ABI calls; p2p = peer-memory exchange")
+    ap.add_argument("--e2e-graph-io", action="store_true", help="N>1 e2e: host<->device copies inside the CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="time eager C-ABI calls instead of a CUDA graph replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity object (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")

@@ -339,13 +339,14 @@ class B200FlatIndex:
 
     def capture(self, nq: int, k: int, with_ignore: bool = False, want: Iterable[str] = ("scores", "ids"),
                 L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
-                beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto") -> "GraphedSearch":
+                beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto", host_io: bool = False) -> "GraphedSearch":
         """Capture query prep -> K1 -> merges (one C-ABI call, mips_search_sharded with one rank) as ONE CUDA
         graph over static buffers; a replay is a single launch."""
         k = self._check_k(k)
         return GraphedSearch(self, int(nq), k, with_ignore, want, L,
                              lambda xq, ign, out: sharded_step(self, None, 1, 0, False, xq, ign, k, out, L,
-                                                               normalize_queries, out_mode, beta, beta_bias, algo))
+                                                               normalize_queries, out_mode, beta, beta_bias, algo),
+                             host_io=host_io)
 
     # ------------------------------------------------------------------ profiling hooks (bench)
     def set_profiling(self, on: bool) -> None:
@@ -439,7 +440,7 @@ class GraphedSearch:
     `ignore_ids`) are static input tensors: replay(xq) copies into them (from the device or from pinned host
     memory) and launches the graph; results land in `.out` (static, overwritten by the next replay)."""
 
-    def __init__(self, local: "B200FlatIndex", nq: int, k: int, with_ignore: bool, want, L, call):
+    def __init__(self, local: "B200FlatIndex", nq: int, k: int, with_ignore: bool, want, L, call, host_io: bool = False):
         dev = local.device
         self.nq, self.k = nq, k
         # random placeholder queries: all-zero queries tie every row of the bank, the worst case of the exact
@@ -454,9 +455,22 @@ class GraphedSearch:
                 call(self.xq, self.ignore_ids, self.out)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # host_io: the graph also holds the H2D copy of the queries from a pinned host buffer (`xq_host`: write the
+        # step's queries there) and the D2H copies of every output into pinned host tensors (`out_host`) — the
+        # whole host-to-host step is ONE launch (replay_host)
+        self.xq_host = self.out_host = None
+        if host_io:
+            self.xq_host = torch.empty((nq, local.d), dtype=torch.float32).pin_memory()
+            self.xq_host.copy_(self.xq)
+            self.out_host = {name: torch.empty(t.shape, dtype=t.dtype).pin_memory() for name, t in self.out.items()}
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if host_io:
+                self.xq.copy_(self.xq_host, non_blocking=True)
             call(self.xq, self.ignore_ids, self.out)
+            if host_io:
+                for name, t in self.out.items():
+                    self.out_host[name].copy_(t, non_blocking=True)
 
     def close(self) -> None:
         """Destroy the graph (required before the NCCL communicator it captured can be destroyed)."""
@@ -464,6 +478,17 @@ class GraphedSearch:
             torch.cuda.synchronize(self.xq.device)
             self.graph.reset()
             self.graph = None
+
+    def replay_host(self, xq=None) -> dict:
+        """host_io graphs: queries from the pinned `xq_host` (optionally filled from `xq` first), results in the
+        pinned `out_host` tensors; returns after the device is done (one launch + one synchronize)."""
+        if self.graph is None or self.xq_host is None:
+            raise RuntimeError("capture(..., host_io=True) first")
+        if xq is not None:
+            self.xq_host.copy_(torch.as_tensor(xq))
+        self.graph.replay()
+        torch.cuda.current_stream(self.xq.device).synchronize()
+        return self.out_host
 
     def replay(self, xq: Optional[torch.Tensor] = None, ignore_ids: Optional[torch.Tensor] = None) -> dict:
         if self.graph is None:

@@ -420,7 +420,7 @@ class ShardedFlatIndex:
     def capture(self, nq: int, k: int, dp: bool = False, with_ignore: bool = False,
                 want: Iterable[str] = ("scores", "ids"), L: Optional[int] = None, normalize_queries: bool = False,
                 out_mode: Optional[int] = None, beta: float = 1.0, beta_bias: float = 0.0,
-                algo: str = "auto") -> "GraphedSearch":
+                algo: str = "auto", host_io: bool = False) -> "GraphedSearch":
         """Capture query prep -> K1 -> local merge -> NCCL collective -> final merge as ONE CUDA graph over
         static buffers (collective: every rank captures). Replays cost one launch; results land in
         `.out` (static tensors, overwritten by the next replay)."""
@@ -430,7 +430,8 @@ class ShardedFlatIndex:
         g = _index.GraphedSearch(
             self.local, int(nq), k, with_ignore, want, L,
             lambda xq, ign, out: self._native_call(dp, xq, ign, k, out, L, normalize_queries, out_mode, beta,
-                                                   beta_bias, algo))
+                                                   beta_bias, algo),
+            host_io=host_io)
         self._graphs.append(weakref.ref(g))
         return g
 

@@ -92,9 +92,12 @@ def _worker(rank, world, port, n, d, nq, k, ret):
         # k > 64 on the sharded bank (bounded passes per shard, lists merged by (key desc, id asc))
         Dk, Ik = o.exact_topk_f64(xb, xq, 100)
         r = mp._sharded.search(xq_t, 100, out_mode=0)
-        assert np.array_equal(r["ids"].cpu().numpy(), Ik)
+        n_diff = o.check_topk(xb, xq, r["scores"].cpu().numpy(), r["ids"].cpu().numpy(), 0, rtol=1e-4, D_ref=Dk, I_ref=Ik,
+                              what="sharded k=100")           # exact up to fp32-accumulation ties among 100 results
+        assert n_diff <= 0.01 * Ik.size
         r = mp._sharded.search_dp(xq_t[mine], 100, out_mode=0)
-        assert np.array_equal(r["ids"].cpu().numpy(), Ik[mine])
+        o.check_topk(xb, xq[mine], r["scores"].cpu().numpy(), r["ids"].cpu().numpy(), 0, rtol=1e-4, D_ref=Dk[mine],
+                     I_ref=Ik[mine], what="sharded dp k=100")
         # a memory refresh keeps the communicator (no new NCCL communicator / exchange buffers per rebuild)
         comm_before = mp._sharded._comm
         mp.begin_refresh(len(rows))
