@@ -53,7 +53,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 2) copy_mix
     const int64_t* __restrict__ copy_seq,   // [R / rows_per_batch, S]
     int rows_per_batch, int V, int S, float eps, float* __restrict__ out,
     float* __restrict__ stats) {            // [R, 2] row max and sum of exp(logits - max) for the backward, or null
-  extern __shared__ float row[];            // this CTA's half of the vocabulary row
+  extern __shared__ __align__(16) float row_raw[];   // this CTA's half of the vocabulary row (+ up to 3 floats of shift)
   __shared__ float red[THREADS / 32];
   __shared__ float peer_val[2];             // written by the peer CTA: its half's max, then its half's sum
   const uint32_t rank = ptx::cluster_ctarank(), peer = rank ^ 1u;
@@ -62,19 +62,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 2) copy_mix
   const int v0 = static_cast<int>(rank) * half, n = min(V, v0 + half) - v0;   // vocabulary slice [v0, v0 + n)
   const float* src = logits + r * V + v0;
   float mx = -CUDART_INF_F;
-  // 8 independent loads in flight per thread (a rolled loop keeps ~1: 4 KB in flight per SM starves HBM)
-  for (int vb = threadIdx.x; vb < n; vb += 8 * THREADS) {
-    float x[8];
+  // Rows of an odd vocabulary (BART / LED: 50,265) are only 4-byte aligned, but every row has a 16-byte aligned
+  // interior: `head` scalars, then 16-byte loads (4 in flight per thread = 32 KB per CTA: the scalar version kept
+  // 16 KB in flight per CTA and sat at 46 % of the copy peak, latency bound), then < 4 tail scalars. The shared row is
+  // shifted by (4 - head) % 4 floats so that the vector stores into it are aligned too.
+  const int head = min(n, static_cast<int>((4u - ((reinterpret_cast<uintptr_t>(src) >> 2) & 3u)) & 3u));
+  float* row = row_raw + ((4 - head) & 3);
+  const int n4 = (n - head) >> 2;
+  const float4* src4 = reinterpret_cast<const float4*>(src + head);
+  for (int ib = threadIdx.x; ib < n4; ib += 4 * THREADS) {
+    float4 x[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int v = vb + i * THREADS;
-      x[i] = v < n ? __ldg(src + v) : -CUDART_INF_F;
+    for (int i = 0; i < 4; ++i) {
+      const int j = ib + i * THREADS;
+      x[i] = j < n4 ? __ldg(src4 + j) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int v = vb + i * THREADS;
-      if (v < n) row[v] = x[i];
-      mx = fmaxf(mx, x[i]);
+    for (int i = 0; i < 4; ++i) {
+      const int j = ib + i * THREADS;
+      if (j < n4) *reinterpret_cast<float4*>(row + head + 4 * j) = x[i];
+      mx = fmaxf(fmaxf(mx, fmaxf(x[i].x, x[i].y)), fmaxf(x[i].z, x[i].w));
+    }
+  }
+  {
+    const int tail0 = head + 4 * n4;                 // scalars: [0, head) and [tail0, n)
+    const int t = static_cast<int>(threadIdx.x);
+    const int v = t < head ? t : tail0 + (t - head);
+    if (v < n && (t < head || v >= tail0)) {
+      const float x = __ldg(src + v);
+      row[v] = x;
+      mx = fmaxf(mx, x);
     }
   }
   mx = block_reduce(mx, red, true);

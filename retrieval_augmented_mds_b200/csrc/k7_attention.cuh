@@ -151,7 +151,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 2) copy_mix
     float* __restrict__ dlogits,            // [R, V]
     float* __restrict__ dgate,              // [R]
     float* __restrict__ dcopy) {            // [R, S]
-  extern __shared__ float row[];            // dM of this CTA's half of the vocabulary row
+  extern __shared__ __align__(16) float row_raw[];   // dM of this CTA's half of the vocabulary row (+ shift)
   __shared__ float red[THREADS / 32];
   __shared__ float peer_val[1];
   const uint32_t rank = ptx::cluster_ctarank(), peer = rank ^ 1u;
@@ -164,23 +164,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 2) copy_mix
   const float* o = out + r * V + v0;
   const float* d = dout + r * V + v0;
   float dot = 0.f;
-  for (int vb = threadIdx.x; vb < n; vb += 4 * THREADS) {
-    float zz[4], oo[4], dd[4];
+  // 16-byte loads over the aligned interior of the (4-byte aligned) rows when the three arrays share the
+  // alignment, which they do for contiguous tensors (k6_mixture.cuh); scalars otherwise and at the two ends
+  const uintptr_t az = reinterpret_cast<uintptr_t>(z), ao = reinterpret_cast<uintptr_t>(o), ad = reinterpret_cast<uintptr_t>(d);
+  const bool vec_ok = ((az ^ ao) & 15u) == 0 && ((az ^ ad) & 15u) == 0;
+  const int head = vec_ok ? min(n, static_cast<int>((4u - ((az >> 2) & 3u)) & 3u)) : n;
+  float* row = row_raw + ((4 - (vec_ok ? head : 0)) & 3);
+  const int n4 = vec_ok ? (n - head) >> 2 : 0;
+  const float4* z4 = reinterpret_cast<const float4*>(z + head);
+  const float4* o4 = reinterpret_cast<const float4*>(o + head);
+  const float4* d4 = reinterpret_cast<const float4*>(d + head);
+  for (int ib = threadIdx.x; ib < n4; ib += 2 * THREADS) {
+    float4 zz[2], oo[2], dd[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int v = vb + i * THREADS;
-      zz[i] = v < n ? __ldg(z + v) : 0.f;
-      oo[i] = v < n ? __ldg(o + v) : 0.f;
-      dd[i] = v < n ? __ldg(d + v) : 0.f;
+    for (int i = 0; i < 2; ++i) {
+      const int j = ib + i * THREADS;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      zz[i] = j < n4 ? __ldg(z4 + j) : zero;
+      oo[i] = j < n4 ? __ldg(o4 + j) : zero;
+      dd[i] = j < n4 ? __ldg(d4 + j) : zero;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int v = vb + i * THREADS;
-      if (v < n) {
-        const float dm = dd[i] * __expf(-oo[i]);
-        row[v] = dm;
-        dot += dm * (__expf(zz[i] - mx) * inv_sum);
+    for (int i = 0; i < 2; ++i) {
+      const int j = ib + i * THREADS;
+      if (j < n4) {
+        float4 dm;
+        dm.x = dd[i].x * __expf(-oo[i].x);
+        dm.y = dd[i].y * __expf(-oo[i].y);
+        dm.z = dd[i].z * __expf(-oo[i].z);
+        dm.w = dd[i].w * __expf(-oo[i].w);
+        *reinterpret_cast<float4*>(row + head + 4 * j) = dm;
+        dot += dm.x * (__expf(zz[i].x - mx) * inv_sum) + dm.y * (__expf(zz[i].y - mx) * inv_sum) +
+               dm.z * (__expf(zz[i].z - mx) * inv_sum) + dm.w * (__expf(zz[i].w - mx) * inv_sum);
       }
+    }
+  }
+  {
+    const int tail0 = head + 4 * n4;                 // scalars: [0, head) and [tail0, n) (everything when !vec_ok)
+    for (int t = threadIdx.x; t < head + (n - tail0); t += THREADS) {
+      const int v = t < head ? t : tail0 + (t - head);
+      const float dm = __ldg(d + v) * __expf(-__ldg(o + v));
+      row[v] = dm;
+      dot += dm * (__expf(__ldg(z + v) - mx) * inv_sum);
     }
   }
   dot = block_reduce(dot, red, false);

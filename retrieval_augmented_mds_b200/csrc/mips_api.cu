@@ -1404,9 +1404,9 @@ static int mixture_device(const float* logits) {
     return set_err(MIPS_E_INVALID, "logits must be device memory");
   CUDA_TRY(cudaSetDevice(pa.device));
   CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                mix::MAX_HALF * static_cast<int>(sizeof(float))));
+                                (mix::MAX_HALF + 4) * static_cast<int>(sizeof(float))));
   CUDA_TRY(cudaFuncSetAttribute(mix::copy_mixture_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                mix::MAX_HALF * static_cast<int>(sizeof(float))));
+                                (mix::MAX_HALF + 4) * static_cast<int>(sizeof(float))));
   return 0;
 }
 
@@ -1422,7 +1422,7 @@ int mips_copy_mixture_fwd(const float* logits, const float* gen_gate, const floa
   if (n_rows > 0x3fffffff) return set_err(MIPS_E_INVALID, "too many rows");
   int rc = mixture_device(logits);
   if (rc) return rc;
-  mix::copy_mixture_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS, static_cast<size_t>((V + 1) / 2) * sizeof(float),
+  mix::copy_mixture_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS, static_cast<size_t>((V + 1) / 2 + 4) * sizeof(float),
                              static_cast<cudaStream_t>(stream)>>>(logits, gen_gate, copy_probs, copy_seq,
                                                                   rows_per_batch, V, S, eps, out, stats);
   LAUNCH_CHECK("copy_mixture_kernel");
@@ -1449,7 +1449,7 @@ int mips_copy_mixture_bwd(const float* logits, const float* out, const float* do
   int rc = mixture_device(logits);
   if (rc) return rc;
   mix::copy_mixture_bwd_kernel<<<static_cast<unsigned>(2 * n_rows), mix::THREADS,
-                                 static_cast<size_t>((V + 1) / 2) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+                                 static_cast<size_t>((V + 1) / 2 + 4) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       logits, out, dout, gen_gate, stats, copy_seq, rows_per_batch, V, S, dlogits, dgate, dcopy);
   LAUNCH_CHECK("copy_mixture_bwd_kernel");
   return 0;
