@@ -63,6 +63,15 @@ static int env_int(const char* name, int dflt) {
 
 constexpr int kProfSlots = 256;
 
+// K1 timing events: on a capturing stream the record becomes an EXTERNAL event-record node of the graph (the event
+// is re-recorded by every replay and can be read with cudaEventElapsedTime afterwards)
+static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+    return cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+  return cudaEventRecord(ev, st);
+}
+
 struct mips_index_s {
   int d = 0, d_pad = 0, metric = 0, dtype = 0, device = 0;
   int64_t ntotal = 0, capacity = 0;
@@ -836,7 +845,7 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
   const bool use_tc = algo == MIPS_ALGO_TC || algo == MIPS_ALGO_TC128;
   int n_parts = 0;
   const int slot = h->prof_n % kProfSlots;
-  if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0[slot], st));
+  if (h->profiling) CUDA_TRY(prof_record(h->ev0[slot], st));
 
   if (algo == MIPS_ALGO_TCX) {
     // exact fp32 search: tensor-core filter over the bf16 shadow, exact re-rank, certificate, and
@@ -878,7 +887,7 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     rc = launch_simt(h, nq, k, ign_local, l2, tile_flag, st, &n_parts);
     if (rc) return rc;
     if (h->profiling) {
-      CUDA_TRY(cudaEventRecord(h->ev1[slot], st));
+      CUDA_TRY(prof_record(h->ev1[slot], st));
       h->prof_n++;
     }
     rc = launch_merge_local(h, h->part_key, h->part_ids, h->norm2, n_parts, nq, k, k, id_offset, out_key, out_ids,
@@ -904,7 +913,7 @@ static int search_chunk(mips_index_s* h, const float* q, int nq, int k, int q_no
     h->last_algo = "simt";
   }
   if (h->profiling) {
-    CUDA_TRY(cudaEventRecord(h->ev1[slot], st));
+    CUDA_TRY(prof_record(h->ev1[slot], st));
     h->prof_n++;
   }
 

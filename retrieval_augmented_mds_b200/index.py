@@ -463,21 +463,36 @@ class GraphedSearch:
             self.xq_host = torch.empty((nq, local.d), dtype=torch.float32).pin_memory()
             self.xq_host.copy_(self.xq)
             self.out_host = {name: torch.empty(t.shape, dtype=t.dtype).pin_memory() for name, t in self.out.items()}
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            if host_io:
+        self._call, self._host_io = call, host_io
+        self.replicas = []
+        self.graph = self._capture_one()
+
+    def _capture_one(self):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            if self._host_io:
                 self.xq.copy_(self.xq_host, non_blocking=True)
-            call(self.xq, self.ignore_ids, self.out)
-            if host_io:
+            self._call(self.xq, self.ignore_ids, self.out)
+            if self._host_io:
                 for name, t in self.out.items():
                     self.out_host[name].copy_(t, non_blocking=True)
+        return g
+
+    def add_replicas(self, n: int) -> list:
+        """n more graphs of the same step over the same static buffers. With profiling on (set_profiling) every
+        capture records its own pair of timing events around K1, so a loop over [graph] + replicas leaves one K1
+        duration per step (bench.py's roofline measurement inside the timed region)."""
+        for _ in range(n):
+            self.replicas.append(self._capture_one())
+        return [self.graph] + self.replicas
 
     def close(self) -> None:
         """Destroy the graph (required before the NCCL communicator it captured can be destroyed)."""
         if self.graph is not None:
             torch.cuda.synchronize(self.xq.device)
-            self.graph.reset()
-            self.graph = None
+            for g in [self.graph] + self.replicas:
+                g.reset()
+            self.graph, self.replicas = None, []
 
     def replay_host(self, xq=None) -> dict:
         """host_io graphs: queries from the pinned `xq_host` (optionally filled from `xq` first), results in the
