@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     int stage_cap = 0,                            // shared-memory staging entries per warp (dynamic smem: 8 bytes per
                                                   // entry LOCAL, 16 bytes FINAL); 0 = read candidates from global memory
     XchgOut xo = XchgOut{nullptr, nullptr, nullptr, 0u, 0},   // LOCAL: publish to the peers
-    XchgIn xi = XchgIn{nullptr, 0u, 0, nullptr, 0ull}) {     // FINAL: wait for the peers
+    XchgIn xi = XchgIn{nullptr, 0u, 0, nullptr, 0ull},       // FINAL: wait for the peers
+    int cut_above = 512) {                                    // LOCAL: radix-cut the staged set when it is larger
   // 2 * MIPS_MAX_K: the candidate merge of the exact fp32 search keeps up to 128 entries per query
   __shared__ float s_key[4][2 * MIPS_MAX_K];
   __shared__ float s_xn2[4][2 * MIPS_MAX_K];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(
     __syncwarp();
   }
   int C_eff = C;
-  if (LOCAL && staged && C > 512) {
+  if (LOCAL && staged && C > cut_above) {
     // Cut the staged candidates down to the k_out best (plus ties at the cut) BEFORE the ordered
     // selection rounds (148 splits x 64 entries x 64 rounds took 3.7 ms for 128 queries): a 4-pass, 8-bit MSB
     // radix select on the order-preserving integer image of the keys finds the k_out-th largest key T in

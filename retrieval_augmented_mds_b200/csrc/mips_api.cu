@@ -789,10 +789,12 @@ static int launch_merge_local(mips_index_s* h, const float* part_key, const int*
   else if (C > 6144 && C <= 12288) { cap = C; wpb = 2; }
   else if (C > 12288 && C <= 24576) { cap = C; wpb = 1; }
   const size_t smem = static_cast<size_t>(wpb) * cap * sizeof(uint2);
+  static const int k2_cut = env_int("MIPS_K2_CUT", 512);   // tuning: staged sets larger than this are radix-cut first
   merge_topk_kernel<true><<<(nq + wpb - 1) / wpb, 32 * wpb, smem, st>>>(
       part_key, part_ids, nullptr, bank_xn2, n_parts, nq, k_in, k_out, id_offset, nullptr, h->metric, MIPS_OUT_IP,
       0.f, nullptr, out_key, out_ids, out_xn2, nullptr, nullptr, 1.f, 0.f, nullptr, 0, nullptr,
-      static_cast<PackedCand*>(out_packed), q_active, cap, xo ? *xo : XchgOut{nullptr, nullptr, nullptr, 0u, 0});
+      static_cast<PackedCand*>(out_packed), q_active, cap, xo ? *xo : XchgOut{nullptr, nullptr, nullptr, 0u, 0},
+      XchgIn{nullptr, 0u, 0, nullptr, 0ull}, k2_cut);
   LAUNCH_CHECK(what);
   return 0;
 }
