@@ -153,3 +153,36 @@ def test_weighted_ranges_tile_the_bank_and_follow_the_weights():
     assert sizes[2] > sizes[0] > sizes[1] and abs(sizes[2] / sizes[1] - 1.05 / 0.95) < 1e-3
     with pytest.raises(ValueError):
         weighted_ranges(10, [0, 0])
+
+
+def test_finalize_lists_matches_merge_kernel_contract(golden):
+    """finalize_lists = the output transform of the merge kernel spelled with tensor ops (used for k > 64, where the
+    lists are longer than one kernel pass holds): against the reference's doc-score statements (golden) and the
+    oracle's metric transforms, on CPU tensors."""
+    from retrieval_augmented_mds_b200.index import finalize_lists
+    g = golden["doc_scores"]
+    q, docs = torch.from_numpy(g["query"]), torch.from_numpy(g["docs"])            # [B, d], [B, k, d]
+    B, k, _ = docs.shape
+    L = int(g["memory_seq_len"])
+    ip = (q[:, None, :] * docs).sum(-1)
+    xn2, qn2 = (docs ** 2).sum(-1), (q ** 2).sum(-1)
+    ids = torch.arange(B * k).view(B, k)
+    out = finalize_lists(ip, ids, xn2, qn2, 0, None, 0.0, ("scores", "ids", "cosine", "doc_prob", "memory_bias"), L, 1.5, -0.25)
+    np.testing.assert_allclose(out["scores"].numpy(), ip.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(out["cosine"].numpy(), g["mips_scores"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["memory_bias"].numpy(), g["memory_bias"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["doc_prob"].numpy(), o.doc_prob(g["mips_scores"], 1.5, -0.25), rtol=1e-5, atol=1e-6)
+    # L2 metric: the ranking key is <q,x> - |x|^2/2; IndexFlatL2 distances, and the augmented form |q|^2 + phi - 2<q,x>
+    key_l2 = ip - 0.5 * xn2
+    d_l2 = finalize_lists(key_l2, ids, xn2, qn2, 1, 1, 0.0, ("scores", "ids"), None, 1.0, 0.0)["scores"]
+    np.testing.assert_allclose(d_l2.numpy(), ((q[:, None, :] - docs) ** 2).sum(-1).numpy(), rtol=1e-4, atol=1e-4)
+    phi = float(xn2.max())
+    d_aug = finalize_lists(ip, ids, xn2, qn2, 0, 2, phi, ("scores", "ids"), None, 1.0, 0.0)["scores"]
+    np.testing.assert_allclose(d_aug.numpy(), (qn2[:, None] + phi - 2 * ip).numpy(), rtol=1e-5, atol=1e-5)
+    # padding (ids -1): -inf / +inf scores, zero cosine, zero probability mass
+    ids_pad = ids.clone()
+    ids_pad[:, -2:] = -1
+    pad = finalize_lists(ip, ids_pad, xn2, qn2, 0, None, 0.0, ("scores", "ids", "cosine", "doc_prob"), None, 1.0, 0.0)
+    assert torch.isinf(pad["scores"][:, -2:]).all() and (pad["cosine"][:, -2:] == 0).all()
+    assert (pad["doc_prob"][:, -2:] == 0).all()
+    np.testing.assert_allclose(pad["doc_prob"].sum(1).numpy(), 1.0, rtol=1e-5)
