@@ -203,7 +203,7 @@ int mips_prof_count(mips_handle h);
  *             own definition: a first hit at index 0 scores 0, like a row without hits)
  *   out3[2] = mean_b(sum_j (cumsum(pred)_j / (j+1)) * pred_j / counts[b])   average_precision
  * All pointers are device memory; per_query [nq, 3] is scratch that also returns the per-query
- * terms; pred_out [nq, k] is optional. k <= MIPS_MAX_K. Async on `stream`. */
+ * terms; pred_out [nq, k] is optional. k <= MIPS_MAX_K_MULTIPASS. Async on `stream`. */
 int mips_retriever_metrics(const int64_t* ids, int nq, int k, const int64_t* row_aid, int64_t n_rows,
                            const int64_t* query_aid, const float* counts, float* per_query, float* out3,
                            float* pred_out, void* stream);

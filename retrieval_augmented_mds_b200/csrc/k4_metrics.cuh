@@ -19,34 +19,30 @@ __global__ void __launch_bounds__(128) retrieval_metrics_rows_kernel(
   const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= nq) return;
   const int64_t want = query_aid[q];
-  // k <= 64: lane l owns ranks l and l + 32
-  float hit[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int j = lane + 32 * t;
+  // ranks in chunks of 32 (any k: multi-pass searches return more than 64 results); lane l owns rank base + l
+  float n_hits = 0.f, ap = 0.f, cum = 0.f;
+  int first = -1;                                  // argmax of a 0/1 row = index of the first 1, or 0 when there is none
+  for (int base = 0; base < k; base += 32) {
+    const int j = base + lane;
     float h = 0.f;
     if (j < k) {
       const int64_t id = ids[static_cast<size_t>(q) * k + j];
       h = (id >= 0 && id < n_rows && row_aid[id] == want) ? 1.f : 0.f;
       if (pred_out) pred_out[static_cast<size_t>(q) * k + j] = h;
     }
-    hit[t] = h;
-  }
-  const uint32_t m0 = __ballot_sync(0xffffffffu, hit[0] != 0.f), m1 = __ballot_sync(0xffffffffu, hit[1] != 0.f);
-  if (lane != 0) return;
-  const float n_hits = static_cast<float>(__popc(m0) + __popc(m1));
-  // argmax of a 0/1 row = index of the first 1, or 0 when there is none
-  const int first = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : 0);
-  const float rr = first == 0 ? 0.f : 1.f / static_cast<float>(first);   // 1/0 = inf -> masked to 0
-  // precision = cumsum(pred) / arange(1, k+1) * pred, summed
-  float ap = 0.f, cum = 0.f;
-  for (int j = 0; j < k; ++j) {
-    const bool h = j < 32 ? (m0 >> j) & 1u : (m1 >> (j - 32)) & 1u;
-    if (h) {
+    uint32_t m = __ballot_sync(0xffffffffu, h != 0.f);
+    n_hits += static_cast<float>(__popc(m));
+    if (first < 0 && m) first = base + __ffs(m) - 1;
+    // precision = cumsum(pred) / arange(1, k+1) * pred, summed
+    while (m) {
+      const int t = __ffs(m) - 1;
+      m &= m - 1;
       cum += 1.f;
-      ap += cum / static_cast<float>(j + 1);
+      ap += cum / static_cast<float>(base + t + 1);
     }
   }
+  if (lane != 0) return;
+  const float rr = first <= 0 ? 0.f : 1.f / static_cast<float>(first);   // 1/0 = inf -> masked to 0
   const float c = counts[q];
   per_query[3 * q + 0] = n_hits / c;
   per_query[3 * q + 1] = rr;

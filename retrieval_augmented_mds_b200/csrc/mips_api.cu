@@ -1138,7 +1138,8 @@ int mips_search_host(mips_handle h, const float* xq, int nq, int k, int q_normal
 int mips_retriever_metrics(const int64_t* ids, int nq, int k, const int64_t* row_aid, int64_t n_rows,
                            const int64_t* query_aid, const float* counts, float* per_query, float* out3,
                            float* pred_out, void* stream) {
-  if (nq < 0 || k < 1 || k > MIPS_MAX_K) return set_err(MIPS_E_INVALID, "bad nq / k (k must be in [1, %d])", MIPS_MAX_K);
+  if (nq < 0 || k < 1 || k > MIPS_MAX_K_MULTIPASS)
+    return set_err(MIPS_E_INVALID, "bad nq / k (k must be in [1, %d])", MIPS_MAX_K_MULTIPASS);
   if (nq == 0) return 0;
   if (!ids || !row_aid || !query_aid || !counts || !per_query || !out3) return set_err(MIPS_E_INVALID, "null buffers");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -142,6 +142,16 @@ def test_retriever_metrics_edge_cases(cuda_device):
     wb = o.retriever_metrics(rb["pred"].cpu().numpy(), np.full(5, 3.0, np.float32))
     for key in wb:
         assert np.isclose(rb[key], wb[key], rtol=1e-6, atol=1e-7), key
+    # k > 64 (the result lists of a multi-pass search): first hit beyond rank 64 for one query
+    wide = torch.randint(0, 10, (4, 150), dtype=torch.int64).cuda()
+    wide[0] = 1                                                       # aid 1 everywhere ...
+    wide[0, 100] = 5                                                  # ... but one row of aid 0 at rank 101
+    rw = pkg.retriever_metrics(wide, row_aid, torch.zeros(4, dtype=torch.int64).cuda(), torch.full((4,), 7.0).cuda(),
+                               return_pred=True)
+    ww = o.retriever_metrics(rw["pred"].cpu().numpy(), np.full(4, 7.0, np.float32))
+    for key in ww:
+        assert np.isclose(rw[key], ww[key], rtol=1e-6, atol=1e-7), key
+    assert rw["pred"][0].sum().item() == 1.0 and rw["pred"][0, 100].item() == 1.0
 
 
 # ----------------------------------------------------------------------------------------- N2
