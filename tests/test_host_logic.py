@@ -186,3 +186,28 @@ def test_finalize_lists_matches_merge_kernel_contract(golden):
     assert torch.isinf(pad["scores"][:, -2:]).all() and (pad["cosine"][:, -2:] == 0).all()
     assert (pad["doc_prob"][:, -2:] == 0).all()
     np.testing.assert_allclose(pad["doc_prob"].sum(1).numpy(), 1.0, rtol=1e-5)
+
+
+def test_bench_reference_arm_runs_real_steps_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): on a small bank it must run REAL
+    steps — value = queries of a step / measured step time — and print one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, BENCH_REF_BUDGET_S="6", OMP_NUM_THREADS="4")
+    res = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--rows", "150000", "--nq", "64",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mips_queries_per_s" and d["unit"] == "queries/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    nq_s = d["config"]["queries_per_step"]
+    assert abs(d["value"] - nq_s / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]          # nothing extrapolated
+    assert d["ms_per_step"] * d["steps"] * 1e-3 <= d["wall_s"]                              # the steps fit the run
