@@ -341,7 +341,10 @@ class B200FlatIndex:
                 L: Optional[int] = None, normalize_queries: bool = False, out_mode: Optional[int] = None,
                 beta: float = 1.0, beta_bias: float = 0.0, algo: str = "auto", host_io: bool = False) -> "GraphedSearch":
         """Capture query prep -> K1 -> merges (one C-ABI call, mips_search_sharded with one rank) as ONE CUDA
-        graph over static buffers; a replay is a single launch."""
+        graph over static buffers; a replay is a single launch. The graph holds the addresses of the bank shard
+        and of the handle's scratch: capture the LARGEST (nq, k) shape first (a later, larger search regrows the
+        scratch and would leave an earlier graph pointing at freed memory), and capture again after `add` grew
+        the shard or after a refresh."""
         k = self._check_k(k)
         return GraphedSearch(self, int(nq), k, with_ignore, want, L,
                              lambda xq, ign, out: sharded_step(self, None, 1, 0, False, xq, ign, k, out, L,

@@ -423,7 +423,9 @@ class ShardedFlatIndex:
                 algo: str = "auto", host_io: bool = False) -> "GraphedSearch":
         """Capture query prep -> K1 -> local merge -> NCCL collective -> final merge as ONE CUDA graph over
         static buffers (collective: every rank captures). Replays cost one launch; results land in
-        `.out` (static tensors, overwritten by the next replay)."""
+        `.out` (static tensors, overwritten by the next replay). Capture the largest (nq, k) shape first: the
+        graph holds the addresses of the handle's scratch, which a later, larger search regrows (see
+        B200FlatIndex.capture); a refresh (`adopt`) and `close()` release the graphs."""
         if self.exchange not in ("native", "p2p") and self.world > 1:
             raise ValueError("capture needs the native exchange (the C-ABI NCCL step)")
         k = self.local._check_k(k)
