@@ -351,8 +351,9 @@ class ShardedFlatIndex:
         if self.world > 1:
             nq = xq.shape[0]
             packed = torch.stack([key.double(), xn2.double(), ids.double()], 0)      # ids < 2^53: exact in fp64
-            allp = torch.empty((self.world,) + tuple(packed.shape), dtype=torch.float64, device=xq.device)
-            dist.all_gather_into_tensor(allp, packed, group=self.group)
+            allp = torch.empty((self.world * 3, nq, k), dtype=torch.float64, device=xq.device)
+            dist.all_gather_into_tensor(allp, packed, group=self.group)    # concatenation along dim 0, rank major
+            allp = allp.view(self.world, 3, nq, k)
             ck = allp[:, 0].permute(1, 0, 2).reshape(nq, -1).float()
             cx = allp[:, 1].permute(1, 0, 2).reshape(nq, -1).float()
             ci = allp[:, 2].permute(1, 0, 2).reshape(nq, -1).long()

@@ -211,3 +211,70 @@ def test_bench_reference_arm_runs_real_steps_on_cpu():
     nq_s = d["config"]["queries_per_step"]
     assert abs(d["value"] - nq_s / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]          # nothing extrapolated
     assert d["ms_per_step"] * d["steps"] * 1e-3 <= d["wall_s"]                              # the steps fit the run
+
+
+class _OracleShard:
+    """Stand-in for B200FlatIndex on CPU (the local search is CUDA only): the oracle searches this rank's rows, so
+    that the host-side exchange / merge logic of ShardedFlatIndex can run under gloo."""
+
+    dtype, metric_type, phi = "fp32", 0, 0.0
+
+    def __init__(self, rows: np.ndarray, id_offset: int):
+        self.rows, self.id_offset = rows, id_offset
+        self.d = rows.shape[1]
+        self.device = torch.device("cpu")
+
+    def _check_k(self, k, multipass=False):
+        return int(k)
+
+    def search_local_multipass(self, xq, k, ignore_ids=None, normalize_queries=False, algo="auto"):
+        q = xq.numpy()
+        ign = None if ignore_ids is None else ignore_ids.numpy() - self.id_offset
+        D, I = o.exact_topk_f64(self.rows, q, k, 0, ignore=ign)
+        if I.shape[1] < k:                                    # the index pads with id -1 when k exceeds its rows
+            pad = k - I.shape[1]
+            D = np.concatenate([D, np.full((len(q), pad), -np.inf)], 1)
+            I = np.concatenate([I, np.full((len(q), pad), -1, dtype=np.int64)], 1)
+        xn2 = np.where(I >= 0, (self.rows[np.maximum(I, 0)] ** 2).sum(-1), 0.0)
+        ids = np.where(I >= 0, I + self.id_offset, -1)
+        key = np.where(I >= 0, D, -np.inf)
+        return (torch.from_numpy(key.astype(np.float32)), torch.from_numpy(ids.astype(np.int64)),
+                torch.from_numpy(xn2.astype(np.float32)), torch.from_numpy((q ** 2).sum(1).astype(np.float32)))
+
+
+def _bigk_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(23)
+        n, d, nq, k = 700, 24, 12, 100
+        xb = rng.standard_normal((n, d)).astype(np.float32)
+        xb[300:305] = xb[3]                                   # ties across the two shards
+        xq = rng.standard_normal((nq, d)).astype(np.float32)
+        xq[0] = xb[3]
+        rows = sharded.shard_range(n, rank, world)
+        sh = sharded.ShardedFlatIndex(_OracleShard(xb[rows.start:rows.stop], rows.start), exchange="torch")
+        ign = rng.integers(0, n, nq)
+        D_ref, I_ref = o.exact_topk_f64(xb, xq, k, 0, ignore=ign)
+        r = sh.search(torch.from_numpy(xq), k, ignore_ids=torch.from_numpy(ign), want=("scores", "ids", "cosine"))
+        assert np.array_equal(r["ids"].numpy(), I_ref)        # (key desc, id asc) across shards, k > 64
+        np.testing.assert_allclose(r["scores"].numpy(), D_ref, rtol=1e-5, atol=1e-5)
+        B = nq // world
+        mine = slice(rank * B, (rank + 1) * B)
+        r = sh.search_dp(torch.from_numpy(xq[mine]), k, ignore_ids=torch.from_numpy(ign[mine]))
+        assert np.array_equal(r["ids"].numpy(), I_ref[mine])  # every rank its own queries
+        r = sh.search(torch.from_numpy(xq), 690)              # k beyond each shard's rows: -1 padding merges away
+        assert np.array_equal(r["ids"].numpy(), o.exact_topk_f64(xb, xq, 690)[1])
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_large_k_merge_gloo():
+    """k > 64 on a row-sharded bank: per-shard lists (here from the oracle) gathered through torch.distributed and
+    merged by (key descending, id ascending) — replicated and data-parallel queries, ties across shards."""
+    world, port = 2, _free_port()
+    with mp.Manager() as man:
+        ret = man.dict()
+        mp.spawn(_bigk_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
